@@ -1,0 +1,200 @@
+// sph_grid.cu — uniform-grid spatial hash: cell index + histogram, exclusive scan, deterministic
+// counting sort and ping-pong gather of the persistent particle fields.
+//
+// Replaces BaseContainer.init_grid / PrefixSumExecutor.run / reorder_particles
+// (reference base_container.py:495-547).  Differences by design:
+//   * flatten is x-fastest / z-slowest (the reference's z-fastest order is not part of its API);
+//   * in-cell order is made deterministic (ascending previous index == stable counting sort ==
+//     the oracle's order) by a tiny per-cell sort of the scattered permutation, so runs are
+//     bit-reproducible although the histogram ranks come from atomics;
+//   * fields are gathered once into the other half of a ping-pong pair (156 B/particle of traffic
+//     instead of the reference's scatter + copy-back, 304 B/particle).
+#include "sph_kernels.h"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SPH_BLOCK) k_cell_index(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 p = d.pv[i];
+    int flat = flatten(c, cell_of(c, p.x, p.y, p.z));
+    d.grid_id[i] = flat;
+    d.rank[i] = atomicAdd(d.cell_count + flat, 1);
+}
+
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += t;
+    }
+    return v;
+}
+
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+    __shared__ int warp_sums[32];
+    __shared__ int block_total;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = warp_inclusive_scan(v);
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < nw ? warp_sums[lane] : 0;
+        int si = warp_inclusive_scan(s);
+        warp_sums[lane] = si - s;   // exclusive prefix of the warp sums
+        if (lane == 31) block_total = si;
+    }
+    __syncthreads();
+    int res = inc - v + warp_sums[wid];
+    *total = block_total;
+    __syncthreads();
+    return res;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const int* __restrict__ in, int n, int* __restrict__ tile_sums) {
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int s = 0;
+    if (base + SCAN_ITEMS <= n) {
+        const int4* p = reinterpret_cast<const int4*>(in + base);
+        int4 a = p[0], b = p[1];
+        s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    } else {
+        for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) s += in[base + k];
+    }
+    int total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_sums(int* tile_sums, int n_tiles) {
+    // single block: exclusive scan of the tile sums in place
+    int carry = 0;
+    for (int base = 0; base < n_tiles; base += 1024) {
+        int idx = base + threadIdx.x;
+        int v = idx < n_tiles ? tile_sums[idx] : 0;
+        int total;
+        int ex = block_exclusive_scan(v, &total);
+        if (idx < n_tiles) tile_sums[idx] = ex + carry;
+        carry += total;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_final(const int* __restrict__ in, int n, const int* __restrict__ tile_sums,
+                                                            int* __restrict__ out) {
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    int total;
+    int ex = block_exclusive_scan(s, &total) + tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    // out[n] = grand total
+    if (base <= n - 1 && n - 1 < base + SCAN_ITEMS) out[n] = ex;
+}
+
+__global__ void __launch_bounds__(SPH_BLOCK) k_scatter_perm(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    d.perm[d.cell_start[d.grid_id[i]] + d.rank[i]] = i;
+}
+
+// canonical in-cell order: ascending previous index.  One thread per cell; cells hold ~10
+// particles, and the previous order was already sorted, so the insertion sort is nearly a no-op.
+__global__ void __launch_bounds__(SPH_BLOCK) k_sort_cells(Consts c, Dev d) {
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= c.ncell) return;
+    const int s = d.cell_start[cell], e = d.cell_start[cell + 1];
+    for (int a = s + 1; a < e; a++) {
+        int key = d.perm[a];
+        int b = a - 1;
+        while (b >= s && d.perm[b] > key) {
+            d.perm[b + 1] = d.perm[b];
+            b--;
+        }
+        d.perm[b + 1] = key;
+    }
+}
+
+__global__ void __launch_bounds__(SPH_BLOCK) k_gather(Consts c, Dev d, int with_ghost_slot) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= c.N) return;
+    const int i = d.perm[k];
+    d.pv_alt[k] = d.pv[i];
+    d.vm_alt[k] = d.vm[i];
+    d.x0_alt[3 * k + 0] = d.x0[3 * i + 0];
+    d.x0_alt[3 * k + 1] = d.x0[3 * i + 1];
+    d.x0_alt[3 * k + 2] = d.x0[3 * i + 2];
+    d.rho_alt[k] = d.rho[i];
+    d.object_id_alt[k] = d.object_id[i];
+    d.material_alt[k] = d.material[i];
+    d.color_alt[3 * k + 0] = d.color[3 * i + 0];
+    d.color_alt[3 * k + 1] = d.color[3 * i + 1];
+    d.color_alt[3 * k + 2] = d.color[3 * i + 2];
+    d.is_dynamic_alt[k] = d.is_dynamic[i];
+    d.grid_id_alt[k] = d.grid_id[i];
+    d.uid_alt[k] = d.uid[i];
+    if (with_ghost_slot) d.ghost_slot_alt[k] = d.ghost_slot[i];
+}
+
+}  // namespace
+
+// exclusive scan of in[0..n) into out[0..n], out[n] = total
+void sph_exclusive_scan(SphHandle* h, const int* in, int n, int* out) {
+    if (n <= 0) {
+        cudaMemsetAsync(out, 0, sizeof(int), h->stream);
+        return;
+    }
+    const int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, h->stream>>>(in, n, h->d.scan_tmp);
+    k_scan_sums<<<1, 1024, 0, h->stream>>>(h->d.scan_tmp, tiles);
+    k_scan_final<<<tiles, SCAN_THREADS, 0, h->stream>>>(in, n, h->d.scan_tmp, out);
+    h->launches += 3;
+}
+
+template <class T>
+static inline void swap_ptr(T*& a, T*& b) { T* t = a; a = b; b = t; }
+
+int sph_sort_particles(SphHandle* h) {
+    Consts& c = h->c;
+    Dev& d = h->d;
+    cudaStream_t st = h->stream;
+    cudaMemsetAsync(d.cell_count, 0, sizeof(int) * (size_t)c.ncell, st);
+    const int nb = (c.N + SPH_BLOCK - 1) / SPH_BLOCK;
+    if (c.N > 0) {
+        k_cell_index<<<nb, SPH_BLOCK, 0, st>>>(c, d);
+        h->launches++;
+    }
+    sph_exclusive_scan(h, d.cell_count, c.ncell, d.cell_start);
+    if (c.N > 0) {
+        k_scatter_perm<<<nb, SPH_BLOCK, 0, st>>>(c, d);
+        k_sort_cells<<<(c.ncell + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, st>>>(c, d);
+        k_gather<<<nb, SPH_BLOCK, 0, st>>>(c, d, (h->P.flags & SPH_FLAG_SLAB) ? 1 : 0);
+        h->launches += 3;
+        swap_ptr(d.pv, d.pv_alt);
+        swap_ptr(d.vm, d.vm_alt);
+        swap_ptr(d.x0, d.x0_alt);
+        swap_ptr(d.rho, d.rho_alt);
+        swap_ptr(d.object_id, d.object_id_alt);
+        swap_ptr(d.material, d.material_alt);
+        swap_ptr(d.color, d.color_alt);
+        swap_ptr(d.is_dynamic, d.is_dynamic_alt);
+        swap_ptr(d.grid_id, d.grid_id_alt);
+        swap_ptr(d.uid, d.uid_alt);
+        swap_ptr(d.ghost_slot, d.ghost_slot_alt);
+    }
+    h->sorted_valid = true;
+    return cudaGetLastError() == cudaSuccess ? SPH_OK : SPH_E_CUDA;
+}

@@ -1,0 +1,91 @@
+// sph_kernels.h — host-side launchers of every kernel + the block reduction helper.
+#pragma once
+
+#include "sph_common.cuh"
+
+// slots of Dev::red (double), see sph_stream.cu
+enum RedSlot {
+    RED_ERR = 0,        // sum for DFSPH / PCISPH error reductions
+    RED_MASS = 1,       // compute_rigid_body_mass
+    RED_CG_RR = 2,      // sum |r|^2 (numerator of alpha)
+    RED_CG_PAP = 3,     // sum p . Ap
+    RED_CG_RR_NEW = 4,  // sum |r_new|^2 (numerator of beta, cg_error^2)
+    RED_CG_RR_OLD = 5,  // sum |r_old|^2 (denominator of beta)
+    RED_COUNT = 16
+};
+
+#ifdef __CUDACC__
+// sum `v` over the block, one atomicAdd(double) per block
+__device__ __forceinline__ void block_reduce_add(double* dst, double v) {
+    __shared__ double warp_part[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) warp_part[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        double s = lane < nw ? warp_part[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && s != 0.0) atomicAdd(dst, s);
+    }
+    __syncthreads();
+}
+#endif
+
+// sph_grid.cu
+void sph_exclusive_scan(SphHandle* h, const int* in, int n, int* out);
+int sph_sort_particles(SphHandle* h);
+
+// sph_sweeps.cu
+void sph_launch_rigid_volume(SphHandle* h);
+void sph_launch_density(SphHandle* h);
+void sph_launch_pressure_accel(SphHandle* h);
+void sph_launch_temp_pressure_accel(SphHandle* h);
+void sph_launch_surface_tension(SphHandle* h);
+void sph_launch_viscosity(SphHandle* h);
+void sph_launch_dfsph_alpha(SphHandle* h);
+void sph_launch_dfsph_density_derivative(SphHandle* h);
+void sph_launch_dfsph_density_star(SphHandle* h);
+void sph_launch_dfsph_correct_divergence(SphHandle* h);
+void sph_launch_dfsph_correct_density(SphHandle* h);
+void sph_launch_pcisph_density_star(SphHandle* h);
+void sph_launch_cg_prepare1(SphHandle* h);
+void sph_launch_cg_Ap(SphHandle* h);
+void sph_launch_neighbor_count(SphHandle* h, int* counts);
+void sph_launch_neighbor_fill(SphHandle* h, const int* offsets, int* indices);
+
+// sph_stream.cu
+void sph_launch_gravity(SphHandle* h);
+void sph_launch_update_velocity(SphHandle* h);
+void sph_launch_update_position(SphHandle* h);
+void sph_launch_boundary(SphHandle* h, int particle_type);
+void sph_launch_renew_rigid(SphHandle* h);
+void sph_launch_prepare_emitter(SphHandle* h);
+void sph_launch_wcsph_pressure(SphHandle* h);
+void sph_launch_dfsph_kappa_v(SphHandle* h);
+void sph_launch_dfsph_kappa(SphHandle* h);
+void sph_launch_dfsph_divergence_error(SphHandle* h);   // red[RED_ERR] = sum rho0 * drho (fluid)
+void sph_launch_dfsph_density_error(SphHandle* h);      // red[RED_ERR] = sum rho_star - 1 (fluid)
+void sph_launch_pcisph_predict_velocity(SphHandle* h);
+void sph_launch_pcisph_predict_position(SphHandle* h);
+void sph_launch_pcisph_update_pressure(SphHandle* h);
+void sph_launch_pcisph_init_step(SphHandle* h);
+void sph_launch_cg_prepare1_pre(SphHandle* h);
+void sph_launch_cg_prepare2(SphHandle* h);
+void sph_launch_cg_dots(SphHandle* h);
+void sph_launch_cg_update_x(SphHandle* h);
+void sph_launch_cg_update_r(SphHandle* h);
+void sph_launch_cg_update_p(SphHandle* h);
+void sph_launch_cg_prepare_guess(SphHandle* h);
+void sph_launch_cg_velocity_from_x(SphHandle* h);
+void sph_launch_cg_velocity_restore(SphHandle* h);
+void sph_launch_rigid_body_mass(SphHandle* h, int object_id);
+void sph_launch_count_dynamic_rigid(SphHandle* h, int* out_dev);
+void sph_fill_i32(SphHandle* h, int* p, size_t n, int v);
+void sph_fill_f32(SphHandle* h, float* p, size_t n, float v);
+// field <-> dense staging conversion (host layout: [n, comps] f32 / i32)
+int sph_field_to_staging(SphHandle* h, int field, int n);
+int sph_staging_to_field(SphHandle* h, int field, int n);
+void sph_launch_cell_coords(SphHandle* h, int* out, int n);
+void sph_launch_ref_cell_hist(SphHandle* h, int* hist);

@@ -1,0 +1,355 @@
+// sph_sweeps.cu — per-particle neighbour summations ("sweeps"): one thread per particle walks the
+// 27-cell window of the cell-sorted SoA (9 contiguous runs) and accumulates the task's sum.
+//
+// Each kernel replaces one @ti.kernel + its *_task of the reference (cited per kernel); the task
+// bodies are inlined C++ lambdas where upstream passes ti.template() callbacks into
+// for_all_neighbors (base_container.py:549-560).
+#include "sph_kernels.h"
+
+namespace {
+
+__device__ __forceinline__ float mass_of(const Dev& d, int j) { return __ldg(reinterpret_cast<const float*>(d.vm + j) + 3); }
+
+// rigid_body_forces / rigid_body_torques accumulation (base_solver.py:174-187 and twins)
+__device__ __forceinline__ void add_wrench(const Dev& d, int obj, float3 force, float3 at) {
+    if (obj < 0 || obj >= SPH_MAX_OBJECTS) return;
+    const float* st = d.rigid_state + obj * 24;
+    float3 arm = make_float3(at.x - st[3], at.y - st[4], at.z - st[5]);
+    float3 tq = cross3(arm, force);
+    float* w = d.rigid_wrench + obj * 6;
+    atomicAdd(w + 0, force.x); atomicAdd(w + 1, force.y); atomicAdd(w + 2, force.z);
+    atomicAdd(w + 3, tq.x); atomicAdd(w + 4, tq.y); atomicAdd(w + 5, tq.z);
+}
+
+// compute_rigid_particle_volume (base_solver.py:105-123)
+__global__ void __launch_bounds__(SPH_BLOCK) k_rigid_volume(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    if (!(pi.w < 0.0f) || !(pi.y <= c.g_upper)) return;
+    const int obj_i = d.object_id[i];
+    float ret = c.kW;  // W(0)
+    for_all_neighbors(c, d, i, pi, [&](int j, float4, float3, float r2) {
+        if (__ldg(d.object_id + j) == obj_i) ret += kernel_W_q(c, sqrtf(r2) * c.inv_h);
+    });
+    float V = 1.0f / ret;
+    reinterpret_cast<float*>(d.pv + i)[3] = -V;
+    reinterpret_cast<float*>(d.vm + i)[3] = c.rho0 * V;
+}
+
+// compute_density (base_solver.py:521-541)
+__global__ void __launch_bounds__(SPH_BLOCK) k_density(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    if (!(pi.w > 0.0f)) return;
+    float ret = 0.0f;
+    for_all_neighbors(c, d, i, pi, [&](int, float4 pj, float3, float r2) {
+        ret += fabsf(pj.w) * kernel_W_q(c, sqrtf(r2) * c.inv_h);
+    });
+    d.rho[i] = (pi.w * c.kW + ret) * c.rho0;
+}
+
+// compute_pressure_acceleration (base_solver.py:135-187) and, with TEMP, PCISPH's
+// compute_temp_pressure_acceleration (PCISPH.py:74-107: fluid rows, no rigid wrench, output a_p)
+template <bool TEMP>
+__global__ void __launch_bounds__(SPH_BLOCK) k_pressure_accel(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    float4* out = TEMP ? d.a_p : d.acc;
+    bool active = pi.w > 0.0f;
+    if (!TEMP) active = active && d.is_dynamic[i] != 0;
+    if (!active) {
+        out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const float den_i = d.rho[i];
+    const float dpi = d.p[i] / (den_i * den_i);
+    float3 ret = make_float3(0.f, 0.f, 0.f);
+    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+        const float gs = kernel_gradient_scale(c, r2);
+        float coef;
+        if (pj.w > 0.0f) {
+            const float den_j = __ldg(d.rho + j);
+            coef = -mass_of(d, j) * (dpi + __ldg(d.p + j) / (den_j * den_j));
+        } else {
+            coef = -c.rho0 * (-pj.w) * dpi;
+            if (!TEMP && c.has_dynamic_rigid && __ldg(d.is_dynamic + j)) {
+                float3 force = R * (-coef * gs * (c.rho0 * pi.w));
+                add_wrench(d, __ldg(d.object_id + j), force, f3(pi));  // arm from x_i (base_solver.py:185)
+            }
+        }
+        const float s = coef * gs;
+        ret.x = fmaf(s, R.x, ret.x); ret.y = fmaf(s, R.y, ret.y); ret.z = fmaf(s, R.z, ret.z);
+    });
+    out[i] = make_float4(ret.x, ret.y, ret.z, 0.f);
+}
+
+// compute_surface_tension_acceleration (base_solver.py:209-229): a_i += sum
+__global__ void __launch_bounds__(SPH_BLOCK) k_surface_tension(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    if (!(pi.w > 0.0f)) return;
+    const float sm = c.sigma / mass_of(d, i);
+    float3 a = make_float3(0.f, 0.f, 0.f);
+    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+        if (!(pj.w > 0.0f)) return;
+        const float w = r2 > c.diameter2 ? kernel_W_q(c, sqrtf(r2) * c.inv_h) : c.w_diameter;
+        const float s = sm * mass_of(d, j) * w;
+        a.x = fmaf(-s, R.x, a.x); a.y = fmaf(-s, R.y, a.y); a.z = fmaf(-s, R.z, a.z);
+    });
+    float4 acc = d.acc[i];
+    d.acc[i] = make_float4(acc.x + a.x, acc.y + a.y, acc.z + a.z, 0.f);
+}
+
+// compute_viscosity_acceleration_standard (base_solver.py:231-278): a_i += sum / rho0
+__global__ void __launch_bounds__(SPH_BLOCK) k_viscosity(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    if (!(pi.w > 0.0f)) return;
+    const float4 vi = d.vm[i];
+    const float den_i = d.rho[i];
+    float3 a = make_float3(0.f, 0.f, 0.f);
+    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+        const float4 vj = __ldg(d.vm + j);
+        const float v_xy = dot3(make_float3(vi.x - vj.x, vi.y - vj.y, vi.z - vj.z), R);
+        const float gs = kernel_gradient_scale(c, r2);
+        float coef;
+        if (pj.w > 0.0f) {
+            coef = c.visc_cf * ((vi.w + vj.w) * 0.5f) / __ldg(d.rho + j);
+        } else {
+            coef = c.visc_cb * (c.rho0 * (-pj.w)) / den_i;
+        }
+        const float s = coef / (r2 + c.visc_eps) * v_xy * gs;
+        a.x = fmaf(s, R.x, a.x); a.y = fmaf(s, R.y, a.y); a.z = fmaf(s, R.z, a.z);
+        if (!(pj.w > 0.0f) && c.has_dynamic_rigid && __ldg(d.is_dynamic + j)) {
+            float3 force = R * (-s * vi.w * c.inv_rho0);     // -acc * m_i / rho0
+            add_wrench(d, __ldg(d.object_id + j), force, f3(pj));
+        }
+    });
+    float4 acc = d.acc[i];
+    d.acc[i] = make_float4(acc.x + a.x * c.inv_rho0, acc.y + a.y * c.inv_rho0, acc.z + a.z * c.inv_rho0, 0.f);
+}
+
+// DFSPH compute_alpha (DFSPH.py:22-62)
+__global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_alpha(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    if (!(pi.w > 0.0f)) return;
+    float3 grad_i = make_float3(0.f, 0.f, 0.f);
+    float sum_k = 0.0f;
+    for_all_neighbors(c, d, i, pi, [&](int, float4 pj, float3 R, float r2) {
+        const float s = -fabsf(pj.w) * kernel_gradient_scale(c, r2);
+        const float3 g = R * s;
+        if (pj.w > 0.0f) sum_k += dist2(g);
+        grad_i = grad_i + g;
+    });
+    sum_k += dist2(grad_i);
+    d.alpha[i] = sum_k > 1e-5f ? 1.0f / sum_k : 0.0f;
+}
+
+// DFSPH compute_density_derivative (DFSPH.py:65-101) / compute_density_star (:104-126)
+template <bool STAR>
+__global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    if (!(pi.w > 0.0f)) return;
+    const float4 vi = d.vm[i];
+    float delta = 0.0f;
+    int nn = 0;
+    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+        const float4 vj = __ldg(d.vm + j);
+        const float vr = dot3(make_float3(vi.x - vj.x, vi.y - vj.y, vi.z - vj.z), R);
+        delta = fmaf(fabsf(pj.w) * kernel_gradient_scale(c, r2), vr, delta);
+        nn++;
+    });
+    if (STAR) {
+        d.rho_star[i] = fmaxf(d.rho[i] / c.rho0 + c.dt * delta, 1.0f);
+    } else {
+        float adv = fmaxf(delta, 0.0f);
+        if (nn < 20) adv = 0.0f;   // particle deficiency (DFSPH.py:93-95)
+        d.drho[i] = adv;
+    }
+}
+
+// DFSPH correct_divergence_step (DFSPH.py:161-202) / correct_density_error_step (:245-283)
+template <bool DIVERGENCE>
+__global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_correct(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    if (!(pi.w > 0.0f)) return;
+    const float* __restrict__ kappa = DIVERGENCE ? d.kappa_v : d.kappa;
+    const float k_i = kappa[i];
+    const float den_i = d.rho[i];
+    const float ki_rho = k_i / den_i;
+    const float thresh = 1e-5f * c.dt;   // m_eps * dt
+    const bool rigid_on = fabsf(k_i) > thresh;
+    float3 dv = make_float3(0.f, 0.f, 0.f);
+    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+        float s;
+        if (pj.w > 0.0f) {
+            const float k_j = __ldg(kappa + j);
+            if (!(fabsf(k_i + k_j) > thresh)) return;
+            s = pj.w * kernel_gradient_scale(c, r2) * (ki_rho + k_j / __ldg(d.rho + j)) * c.rho0;
+        } else {
+            if (!rigid_on) return;
+            s = (-pj.w) * kernel_gradient_scale(c, r2) * ki_rho * c.rho0;
+            if (c.has_dynamic_rigid && __ldg(d.is_dynamic + j)) {
+                float3 force = R * (s * c.inv_dt * (pi.w * c.rho0));
+                add_wrench(d, __ldg(d.object_id + j), force, f3(pj));
+            }
+        }
+        dv.x = fmaf(-s, R.x, dv.x); dv.y = fmaf(-s, R.y, dv.y); dv.z = fmaf(-s, R.z, dv.z);
+    });
+    float4 v = d.vm[i];
+    d.vm[i] = make_float4(v.x + dv.x, v.y + dv.y, v.z + dv.z, v.w);
+}
+
+// PCISPH compute_density_star (PCISPH.py:32-62): predicted positions, no self term, neighbour
+// set from the current positions.  Accumulates sum max(0, rho*/rho0 - 1) into red[0].
+__global__ void __launch_bounds__(SPH_BLOCK) k_pcisph_density_star(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float err = 0.0f;
+    if (i < c.N) {
+        float4 pi = d.pv[i];
+        if (pi.w > 0.0f) {
+            const float4 xi = d.x_pred[i];
+            float ret = 0.0f;
+            for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3, float) {
+                float4 xj = pj.w > 0.0f ? __ldg(d.x_pred + j) : pj;
+                float r2 = dist2(make_float3(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z));
+                ret += fabsf(pj.w) * kernel_W_q(c, sqrtf(r2) * c.inv_h);
+            });
+            d.rho_star[i] = ret * c.rho0;
+            err = fmaxf(0.0f, ret - 1.0f);
+        }
+    }
+    block_reduce_add(d.red + 0, (double)err);
+}
+
+// implicit viscosity: A_ij = -c (grad W_ij (x) R) / (r^2 + 0.01 h^2)  (base_solver.py:348-371);
+// returns c' such that A_ij = c' * (R (x) R)   (grad W = gs * R)
+__device__ __forceinline__ float visc_A_scale(const Consts& c, const Dev& d, float mi, float den_i, int j, float4 pj, float r2) {
+    const float gs = kernel_gradient_scale(c, r2);
+    float coef;
+    if (pj.w > 0.0f) coef = -c.visc_cf * ((mi + mass_of(d, j)) * 0.5f) / __ldg(d.rho + j);
+    else coef = -c.visc_cb * (c.rho0 * (-pj.w)) / den_i;
+    return coef / (r2 + c.visc_eps) * gs;
+}
+
+// prepare_conjugate_gradient_solver1, the per-particle part (base_solver.py:300-315):
+// D_i^-1, b_i and p_i <- x_i
+__global__ void __launch_bounds__(SPH_BLOCK) k_cg_prepare1(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    if (!(pi.w > 0.0f)) return;
+    const float4 vi = d.vm[i];
+    const float den_i = d.rho[i];
+    // ret = -sum A_ij (symmetric in R (x) R): 6 unique entries
+    float sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    float3 b = make_float3(0.f, 0.f, 0.f);
+    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+        const float a = -visc_A_scale(c, d, vi.w, den_i, j, pj, r2);   // ret -= A_ij
+        sxx = fmaf(a * R.x, R.x, sxx); sxy = fmaf(a * R.x, R.y, sxy); sxz = fmaf(a * R.x, R.z, sxz);
+        syy = fmaf(a * R.y, R.y, syy); syz = fmaf(a * R.y, R.z, syz); szz = fmaf(a * R.z, R.z, szz);
+        if (!(pj.w > 0.0f)) {   // compute_b_i_task :333-346, rigid neighbours only
+            const float4 vj = __ldg(d.vm + j);
+            const float s = c.visc_cb * c.rho0 * (-pj.w) / den_i * dot3(f3(vj), R) / (r2 + c.visc_eps) *
+                            kernel_gradient_scale(c, r2);
+            b.x = fmaf(s, R.x, b.x); b.y = fmaf(s, R.y, b.y); b.z = fmaf(s, R.z, b.z);
+        }
+    });
+    // diag = I - ret * dt / rho0
+    const float f = c.dt * c.inv_rho0;
+    const float m00 = 1.0f - sxx * f, m01 = -sxy * f, m02 = -sxz * f, m11 = 1.0f - syy * f, m12 = -syz * f, m22 = 1.0f - szz * f;
+    const float c00 = m11 * m22 - m12 * m12, c01 = m12 * m02 - m01 * m22, c02 = m01 * m12 - m11 * m02;
+    const float inv = 1.0f / (m00 * c00 + m01 * c01 + m02 * c02);
+    float* o = d.cg_dinv + 9 * (size_t)i;
+    o[0] = c00 * inv; o[1] = c01 * inv; o[2] = c02 * inv;
+    o[3] = c01 * inv; o[4] = (m00 * m22 - m02 * m02) * inv; o[5] = (m02 * m01 - m00 * m12) * inv;
+    o[6] = c02 * inv; o[7] = o[5]; o[8] = (m00 * m11 - m01 * m01) * inv;
+    d.cg_b[i] = make_float4(vi.x - c.dt * b.x * c.inv_rho0, vi.y - c.dt * b.y * c.inv_rho0, vi.z - c.dt * b.z * c.inv_rho0, 0.f);
+    d.cg_p[i] = d.cg_x[i];
+}
+
+// compute_Ap (base_solver.py:373-391): Ap_i = p_i + dt/rho0 * D_i^-1 sum_{fluid j} (-A_ij) p_j
+__global__ void __launch_bounds__(SPH_BLOCK) k_cg_Ap(Consts c, Dev d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    float4 pi = d.pv[i];
+    if (!(pi.w > 0.0f)) return;
+    const float mi = mass_of(d, i);
+    const float den_i = d.rho[i];
+    float3 s = make_float3(0.f, 0.f, 0.f);
+    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+        if (!(pj.w > 0.0f)) return;
+        const float a = -visc_A_scale(c, d, mi, den_i, j, pj, r2);
+        const float4 pj_cg = __ldg(d.cg_p + j);
+        const float t = a * dot3(R, f3(pj_cg));   // (-A_ij) p_j = a R (R . p_j)
+        s.x = fmaf(t, R.x, s.x); s.y = fmaf(t, R.y, s.y); s.z = fmaf(t, R.z, s.z);
+    });
+    const float* m = d.cg_dinv + 9 * (size_t)i;
+    float3 r = make_float3(m[0] * s.x + m[1] * s.y + m[2] * s.z, m[3] * s.x + m[4] * s.y + m[5] * s.z,
+                           m[6] * s.x + m[7] * s.y + m[8] * s.z);
+    const float f = c.dt * c.inv_rho0;
+    const float4 p = d.cg_p[i];
+    d.cg_Ap[i] = make_float4(fmaf(r.x, f, p.x), fmaf(r.y, f, p.y), fmaf(r.z, f, p.z), 0.f);
+}
+
+// |N(i)| per particle / CSR fill (host debug view of for_all_neighbors)
+__global__ void __launch_bounds__(SPH_BLOCK) k_neighbor_count(Consts c, Dev d, int* counts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    int n = 0;
+    for_all_neighbors(c, d, i, d.pv[i], [&](int, float4, float3, float) { n++; });
+    counts[i] = n;
+}
+__global__ void __launch_bounds__(SPH_BLOCK) k_neighbor_fill(Consts c, Dev d, const int* offsets, int* indices) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    int o = offsets[i];
+    for_all_neighbors(c, d, i, d.pv[i], [&](int j, float4, float3, float) { indices[o++] = j; });
+}
+
+}  // namespace
+
+#define LAUNCH(kernel)                                                        \
+    do {                                                                      \
+        if (h->c.N > 0) {                                                     \
+            kernel<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d); \
+            h->launches++;                                                    \
+        }                                                                     \
+    } while (0)
+
+void sph_launch_rigid_volume(SphHandle* h) { LAUNCH(k_rigid_volume); }
+void sph_launch_density(SphHandle* h) { LAUNCH(k_density); }
+void sph_launch_pressure_accel(SphHandle* h) { LAUNCH(k_pressure_accel<false>); }
+void sph_launch_temp_pressure_accel(SphHandle* h) { LAUNCH(k_pressure_accel<true>); }
+void sph_launch_surface_tension(SphHandle* h) { LAUNCH(k_surface_tension); }
+void sph_launch_viscosity(SphHandle* h) { LAUNCH(k_viscosity); }
+void sph_launch_dfsph_alpha(SphHandle* h) { LAUNCH(k_dfsph_alpha); }
+void sph_launch_dfsph_density_derivative(SphHandle* h) { LAUNCH(k_dfsph_density_change<false>); }
+void sph_launch_dfsph_density_star(SphHandle* h) { LAUNCH(k_dfsph_density_change<true>); }
+void sph_launch_dfsph_correct_divergence(SphHandle* h) { LAUNCH(k_dfsph_correct<true>); }
+void sph_launch_dfsph_correct_density(SphHandle* h) { LAUNCH(k_dfsph_correct<false>); }
+void sph_launch_pcisph_density_star(SphHandle* h) { LAUNCH(k_pcisph_density_star); }
+void sph_launch_cg_prepare1(SphHandle* h) { LAUNCH(k_cg_prepare1); }
+void sph_launch_cg_Ap(SphHandle* h) { LAUNCH(k_cg_Ap); }
+
+void sph_launch_neighbor_count(SphHandle* h, int* counts) {
+    if (h->c.N <= 0) return;
+    k_neighbor_count<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d, counts);
+    h->launches++;
+}
+void sph_launch_neighbor_fill(SphHandle* h, const int* offsets, int* indices) {
+    if (h->c.N <= 0) return;
+    k_neighbor_fill<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d, offsets, indices);
+    h->launches++;
+}

@@ -1,0 +1,313 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Integer / index work is compared bit-exactly (cell coordinates, per-cell counts, neighbour sets,
+iteration counts); floating-point fields within the tolerances written next to each assertion
+(north_star: particle positions within 1e-4 relative after N steps).
+"""
+import numpy as np
+import pytest
+
+from helpers import by_uid, make_sim, oracle_library, scene
+
+pytestmark = pytest.mark.gpu
+
+
+def small_scene(method, **kw):
+    base = dict(domain_end=(0.6, 0.8, 0.6), block_start=(0.1, 0.1, 0.1), block_end=(0.3, 0.5, 0.3),
+                velocity=(0.0, -1.0, 0.0))
+    base.update(kw)
+    return scene(method, **base)
+
+
+def jitter(c, seed=0, amp=0.006, vel=0.5):
+    """Same perturbation on any backend (applied in uid order)."""
+    n = c.particle_num[None]
+    rng = np.random.default_rng(seed)
+    uid = c.particle_uids.to_numpy(n)
+    x = by_uid(c, c.particle_positions)
+    mat = by_uid(c, c.particle_materials)
+    nf = int((mat == 1).sum())
+    x[mat == 1] += rng.uniform(-amp, amp, size=(nf, 3)).astype(np.float32)
+    v = rng.normal(0, vel, size=(n, 3)).astype(np.float32)
+    v[mat != 1] = 0
+    c.particle_positions.from_numpy(x[uid])
+    c.particle_velocities.from_numpy(v[uid])
+    c.prepare_neighborhood_search()
+
+
+def pair(method, jittered=True, **kw):
+    sc = small_scene(method, **kw)
+    g = make_sim(sc)
+    o = make_sim(sc, oracle_library())
+    if jittered:
+        for c, s in (g, o):
+            jitter(c)
+            s.compute_rigid_particle_volume()
+    return g, o
+
+
+def close(cg, co, name, rtol, atol_scale=1e-6, mask=None):
+    a, b = by_uid(cg, getattr(cg, name)).astype(np.float64), by_uid(co, getattr(co, name)).astype(np.float64)
+    if mask is not None:
+        a, b = a[mask], b[mask]
+    scale = np.abs(b).max() if b.size else 1.0
+    ok = np.allclose(a, b, rtol=rtol, atol=atol_scale * scale)
+    assert ok, f"{name}: max abs diff {np.abs(a - b).max():.3e} (scale {scale:.3e})"
+
+
+def fluid_mask(c):
+    return by_uid(c, c.particle_materials) == 1
+
+
+def test_backend_is_cuda():
+    (cg, sg), _ = pair("wcsph", jittered=False)
+    assert cg.engine.backend == "cuda-sm100a"
+
+
+def test_cells_counts_and_neighbor_sets_bit_exact():
+    (cg, sg), (co, so) = pair("wcsph")
+    from sph_project_b200._native import F
+    n = cg.particle_num[None]
+    # same multiset of particles, uid is a permutation
+    assert np.array_equal(np.sort(cg.particle_uids.to_numpy(n)), np.arange(n))
+    # cell coordinates trunc(x / h)
+    cell_g = np.empty((n, 3), np.int32); cell_g[cg.particle_uids.to_numpy(n)] = cg.engine.get_field(F.CELL, n)
+    cell_o = np.empty((n, 3), np.int32); cell_o[co.particle_uids.to_numpy(n)] = co.engine.get_field(F.CELL, n)
+    assert np.array_equal(cell_g, cell_o)
+    # per-cell counts, reference flatten, inclusive scan (grid_num_particles after the prefix sum)
+    assert np.array_equal(cg.grid_num_particles.to_numpy(), co.grid_num_particles.to_numpy())
+    # the library's own order: grid ids ascending, in-cell order = ascending previous index (stable)
+    gid = cg.grid_ids.to_numpy(n)
+    assert np.all(np.diff(gid) >= 0)
+    # neighbour sets as sets of uid pairs
+    def uid_pairs(c):
+        off, idx = c.neighbor_lists()
+        uid = c.particle_uids.to_numpy(n).astype(np.int64)
+        rows = np.repeat(np.arange(n), np.diff(off))
+        return np.sort(uid[rows] * n + uid[idx])
+    assert np.array_equal(uid_pairs(cg), uid_pairs(co))
+    cnt_g = np.empty(n, np.int32); cnt_g[cg.particle_uids.to_numpy(n)] = cg.engine.get_field(F.NEIGHBOR_COUNT, n)
+    cnt_o = np.empty(n, np.int32); cnt_o[co.particle_uids.to_numpy(n)] = co.engine.get_field(F.NEIGHBOR_COUNT, n)
+    assert np.array_equal(cnt_g, cnt_o)
+
+
+def test_sort_is_stable_like_the_oracle():
+    """Within a cell the order is ascending previous index, i.e. uid order right after insertion."""
+    (cg, sg), _ = pair("wcsph", jittered=False)
+    n = cg.particle_num[None]
+    gid, uid = cg.grid_ids.to_numpy(n), cg.particle_uids.to_numpy(n)
+    same = gid[1:] == gid[:-1]
+    assert np.all(uid[1:][same] > uid[:-1][same])
+
+
+def test_wcsph_kernels():
+    (cg, sg), (co, so) = pair("wcsph")
+    fl = fluid_mask(co)
+    close(cg, co, "particle_rest_volumes", 2e-6)
+    close(cg, co, "particle_masses", 2e-6)
+    for s in (sg, so):
+        s.compute_density()
+    close(cg, co, "particle_densities", 3e-6, mask=fl)
+    for c, s in ((cg, sg), (co, so)):      # compress so that pressure is non-zero
+        n = c.particle_num[None]
+        c.particle_densities.from_numpy(c.particle_densities.to_numpy(n) * np.float32(1.3))
+        s.compute_pressure()
+    close(cg, co, "particle_pressures", 2e-5, atol_scale=1e-6, mask=fl)
+    for s in (sg, so):
+        s.compute_pressure_acceleration()
+    close(cg, co, "particle_accelerations", 1e-4, atol_scale=2e-6)
+    for s in (sg, so):
+        s.compute_gravity_acceleration()
+        s.compute_surface_tension_acceleration()
+    close(cg, co, "particle_accelerations", 1e-5, atol_scale=1e-6, mask=fl)
+    for s in (sg, so):
+        s.compute_viscosity_acceleration_standard()
+    close(cg, co, "particle_accelerations", 1e-4, atol_scale=2e-6, mask=fl)
+    for s in (sg, so):
+        s.update_fluid_velocity()
+        s.update_fluid_position()
+        s.enforce_domain_boundary_3D(1)
+    close(cg, co, "particle_velocities", 1e-5, atol_scale=1e-6)
+    close(cg, co, "particle_positions", 1e-6)
+
+
+def test_dfsph_kernels():
+    (cg, sg), (co, so) = pair("dfsph", dt=1e-3)
+    fl = fluid_mask(co)
+    for s in (sg, so):
+        s.compute_density()
+        s.compute_alpha()
+    close(cg, co, "particle_densities", 3e-6, mask=fl)
+    close(cg, co, "particle_dfsph_alphas", 2e-5, mask=fl)
+    for s in (sg, so):
+        s.compute_density_derivative()
+        s.compute_density_star()
+    close(cg, co, "particle_densities_derivatives", 1e-4, atol_scale=2e-5, mask=fl)
+    close(cg, co, "particle_densities_star", 1e-5, mask=fl)
+    assert abs(sg.compute_density_derivative_error() - so.compute_density_derivative_error()) <= 1e-4 * abs(so.compute_density_derivative_error()) + 1e-6
+    assert abs(sg.compute_density_error() - so.compute_density_error()) <= 1e-4 * abs(so.compute_density_error()) + 1e-9
+    for s in (sg, so):
+        s.compute_kappa_v()
+        s.correct_divergence_step()
+    close(cg, co, "particle_dfsph_kappa_v", 1e-4, atol_scale=2e-5, mask=fl)
+    close(cg, co, "particle_velocities", 1e-4, atol_scale=2e-6)
+    for s in (sg, so):
+        s.compute_kappa()
+        s.correct_density_error_step()
+    close(cg, co, "particle_dfsph_kappa", 1e-4, atol_scale=2e-5, mask=fl)
+    close(cg, co, "particle_velocities", 1e-4, atol_scale=5e-6)
+
+
+def test_pcisph_kernels():
+    (cg, sg), (co, so) = pair("pcisph", dt=8e-4)
+    fl = fluid_mask(co)
+    assert np.isclose(cg.pcisph_k[None], co.pcisph_k[None], rtol=2e-5)
+    for s in (sg, so):
+        s.compute_density()
+        s.compute_non_pressure_acceleration()
+        s.init_step()
+    close(cg, co, "particle_predicted_positions", 1e-6, mask=fl)
+    for s in (sg, so):
+        s.compute_density_star()
+    close(cg, co, "particle_densities_star", 3e-6, mask=fl)
+    assert np.isclose(cg.density_error[None], co.density_error[None], rtol=1e-4, atol=1e-8)
+    for s in (sg, so):
+        s.update_pressure()
+        s.compute_temp_pressure_acceleration()
+        s.compute_predicted_velocity()
+        s.compute_predicted_position()
+    close(cg, co, "particle_pressures", 1e-4, atol_scale=1e-5, mask=fl)
+    close(cg, co, "particle_pressure_accelerations", 2e-4, atol_scale=1e-5)
+    close(cg, co, "particle_predicted_positions", 1e-6, mask=fl)
+
+
+def test_implicit_viscosity_kernels():
+    (cg, sg), (co, so) = pair("dfsph", dt=1e-3, viscosity_method="implicit", viscosity=50.0, viscosity_b=50.0)
+    fl = fluid_mask(co)
+    for s in (sg, so):
+        s.compute_density()
+        s.prepare_conjugate_gradient_solver1()
+    close(cg, co, "particle_densities", 3e-6, mask=fl)
+    for name in ("cg_b", "cg_p", "original_velocity", "cg_diagnol_ii_inv"):
+        a = by_uid(cg, getattr(sg, name)).astype(np.float64)[fl]
+        b = by_uid(co, getattr(so, name)).astype(np.float64)[fl]
+        assert np.allclose(a, b, rtol=2e-4, atol=2e-5 * np.abs(b).max()), name
+    for s in (sg, so):
+        s.compute_Ap()
+        s.prepare_conjugate_gradient_solver2()
+    a, b = by_uid(cg, sg.cg_r).astype(np.float64)[fl], by_uid(co, so.cg_r).astype(np.float64)[fl]
+    assert np.allclose(a, b, rtol=1e-3, atol=1e-4 * np.abs(b).max())
+    # full solve: converged velocities agree although iteration counts may differ by a few
+    itg, _ = sg._engine.implicit_viscosity_solve()
+    ito, _ = so._engine.implicit_viscosity_solve()
+    assert abs(itg - ito) <= max(3, ito // 5), (itg, ito)
+    close(cg, co, "particle_accelerations", 2e-3, atol_scale=2e-4, mask=fl)
+
+
+@pytest.mark.parametrize("method,dt,steps", [("wcsph", 4e-4, 60), ("pcisph", 8e-4, 40), ("dfsph", 1e-3, 40)])
+def test_trajectory_parity(method, dt, steps):
+    """N-step dam break: positions within 1e-4 relative (north_star), equal iteration counts."""
+    (cg, sg), (co, so) = pair(method, jittered=False, dt=dt)
+    stg, sto = sg.step(steps), so.step(steps)
+    xg, xo = by_uid(cg, cg.particle_positions), by_uid(co, co.particle_positions)
+    rel = np.abs(xg - xo).max() / np.abs(xo).max()
+    assert rel < 1e-4, rel
+    close(cg, co, "particle_velocities", 1e-3, atol_scale=1e-3)
+    assert cg.particle_num[None] == co.particle_num[None]
+    if method == "dfsph":
+        assert abs(stg.total_dfsph_iterations - sto.total_dfsph_iterations) <= 1
+        assert abs(stg.total_dfsph_iterations_v - sto.total_dfsph_iterations_v) <= 1
+        assert stg.dfsph_density_error <= 1e-4 + 1e-9           # solver tolerance (DFSPH.py:20)
+        assert stg.dfsph_divergence_error <= 0.001 * 1000.0 / dt
+    if method == "pcisph":
+        assert abs(stg.total_pcisph_iterations - sto.total_pcisph_iterations) <= 1
+
+
+def test_pressurised_dfsph_iterations_match():
+    """Over-dense start (particles packed at 0.9 spacing) so that both DFSPH solves iterate."""
+    sc = small_scene("dfsph", dt=5e-4)
+    sims = [make_sim(sc), make_sim(sc, oracle_library())]
+    for c, s in sims:
+        n = c.particle_num[None]
+        x = c.particle_positions.to_numpy(n)
+        mat = c.particle_materials.to_numpy(n)
+        lo = x[mat == 1].min(0)
+        x[mat == 1] = lo + (x[mat == 1] - lo) * np.float32(0.88)
+        c.particle_positions.from_numpy(x)
+        c.prepare_neighborhood_search()
+        s.compute_density()
+        s.compute_alpha()
+    (cg, sg), (co, so) = sims
+    stg, sto = sg.step(4), so.step(4)
+    assert sto.total_dfsph_iterations > 4 or sto.total_dfsph_iterations_v > 4   # the case is non-trivial
+    assert abs(stg.total_dfsph_iterations - sto.total_dfsph_iterations) <= 1
+    assert abs(stg.total_dfsph_iterations_v - sto.total_dfsph_iterations_v) <= 1
+    xg, xo = by_uid(cg, cg.particle_positions), by_uid(co, co.particle_positions)
+    assert np.abs(xg - xo).max() / np.abs(xo).max() < 1e-4
+
+
+def test_python_step_path_equals_native_step():
+    """solver._step() (one C-ABI call per upstream kernel) and sph_step() are the same kernels."""
+    sc = small_scene("dfsph", dt=1e-3)
+    ca, sa = make_sim(sc)
+    cb, sb = make_sim(sc)
+    sa.step(3)
+    for _ in range(3):
+        sb._step()
+        sb.compute_rigid_particle_volume()
+    assert np.array_equal(by_uid(ca, ca.particle_positions), by_uid(cb, cb.particle_positions))
+    assert np.array_equal(by_uid(ca, ca.particle_velocities), by_uid(cb, cb.particle_velocities))
+
+
+def test_bitwise_reproducible():
+    sc = small_scene("wcsph")
+    out = []
+    for _ in range(2):
+        c, s = make_sim(sc)
+        s.step(10)
+        n = c.particle_num[None]
+        out.append((c.particle_positions.to_numpy(n), c.particle_uids.to_numpy(n)))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_emitter_and_boundary_edge_cases():
+    """gravitationUpper emitter hack (base_solver.py:651-677) and particles pushed through the walls."""
+    sc = small_scene("wcsph", g_upper=0.35)
+    (cg, sg), (co, so) = make_sim(sc), make_sim(sc, oracle_library())
+    matg = by_uid(cg, cg.particle_materials)
+    assert np.array_equal(matg, by_uid(co, co.particle_materials))
+    block = by_uid(cg, cg.particle_object_ids) == 0
+    assert (matg[block] == 2).any() and (matg[block] == 1).any()   # upper part became emitter ("rigid") particles
+    for c in (cg, co):                   # throw some fluid through the walls
+        n = c.particle_num[None]
+        v = c.particle_velocities.to_numpy(n)
+        m = c.particle_materials.to_numpy(n)
+        u = c.particle_uids.to_numpy(n)
+        v[(m == 1) & (u % 7 == 0)] = np.array([900.0, -700.0, 800.0], np.float32)
+        c.particle_velocities.from_numpy(v)
+    sg.step(30), so.step(30)
+    assert np.array_equal(by_uid(cg, cg.particle_materials), by_uid(co, co.particle_materials))
+    xg, xo = by_uid(cg, cg.particle_positions), by_uid(co, co.particle_positions)
+    assert np.abs(xg - xo).max() / np.abs(xo).max() < 1e-4
+    pad = cg.padding
+    fl = by_uid(cg, cg.particle_materials) == 1
+    assert np.all(xg[fl] >= pad - 1e-6) and np.all(xg[fl] <= np.array([0.6, 0.8, 0.6]) - pad + 1e-6)
+
+
+def test_empty_and_ragged():
+    """No fluid at all (box only), and a late-entry block inserted mid-run through the Python path."""
+    sc = small_scene("wcsph")
+    sc["FluidBlocks"] = []
+    c, s = make_sim(sc)
+    s.step(2)
+    assert c.fluid_particle_num[None] == 0 and c.particle_num[None] == c.particle_max_num
+    late = dict(objectId=1, start=[0.35, 0.3, 0.35], end=[0.45, 0.4, 0.45], translation=[0, 0, 0], scale=[1, 1, 1],
+                velocity=[0, 0, 0], density=1000.0, color=[1, 2, 3], entryTime=0.002)
+    sc = small_scene("dfsph", dt=1e-3, extra_blocks=[late])
+    (cg, sg), (co, so) = make_sim(sc), make_sim(sc, oracle_library())
+    n0 = cg.particle_num[None]
+    for _ in range(6):
+        sg.step(), so.step()
+    assert cg.particle_num[None] == co.particle_num[None] == n0 + 125
+    xg, xo = by_uid(cg, cg.particle_positions), by_uid(co, co.particle_positions)
+    assert np.abs(xg - xo).max() / np.abs(xo).max() < 1e-4
