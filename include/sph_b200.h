@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SPH_ABI_VERSION 3
+#define SPH_ABI_VERSION 4
 #define SPH_MAX_OBJECTS 20 /* base_container.py:52 max_num_object */
 
 /* error codes */
@@ -285,6 +285,19 @@ int sph_pcisph_refine(SphHandle* h, int32_t* iterations, float* error);
 int sph_implicit_viscosity_solve(SphHandle* h, int32_t* iterations, float* error);
 
 int sph_synchronize(SphHandle* h);
+/* Run all work of this handle on the caller's CUDA stream (cudaStream_t as void*; NULL restores the
+ * handle's own stream) so that host frameworks can order / time it with their own events. */
+int sph_set_stream(SphHandle* h, void* cuda_stream);
+
+/* Per-kernel device time: when enabled every kernel launch is bracketed by CUDA events on the
+ * handle's stream; sph_profile_read synchronises, returns one row per kernel name and resets. */
+typedef struct SphKernelStat {
+    char name[56];
+    int64_t launches;
+    double total_ms;
+} SphKernelStat;
+int sph_profile_enable(SphHandle* h, int32_t enable);
+int sph_profile_read(SphHandle* h, SphKernelStat* out, int32_t capacity, int32_t* count);
 
 /* ---- Z-slab sharding (no reference counterpart) ----------------------- */
 /* A slab handle owns cells cz in [z_lo, z_hi) and keeps imported ghost particles of the

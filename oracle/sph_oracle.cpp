@@ -1279,6 +1279,9 @@ int sph_implicit_viscosity_solve(SphHandle* h, int32_t* it, float* e) {
 }
 
 int sph_synchronize(SphHandle*) { return SPH_OK; }
+int sph_set_stream(SphHandle*, void*) { return SPH_OK; }
+int sph_profile_enable(SphHandle*, int32_t) { return SPH_OK; }
+int sph_profile_read(SphHandle*, SphKernelStat*, int32_t, int32_t* count) { if (count) *count = 0; return SPH_OK; }
 
 // Z-slab sharding is a property of the CUDA product; the oracle always holds the whole domain.
 int sph_slab_set_range(SphHandle* h, int32_t, int32_t) { return fail(h, SPH_E_UNSUPPORTED, "oracle holds the whole domain"); }

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_OBJECTS = 20
 
 METHOD_WCSPH, METHOD_PCISPH, METHOD_DFSPH = 0, 1, 2
@@ -46,6 +46,10 @@ class SphStepStats(C.Structure):
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class SphKernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 56), ("launches", C.c_int64), ("total_ms", C.c_double)]
 
 
 class SphSlabInfo(C.Structure):
@@ -168,6 +172,9 @@ PROTOTYPES = {
     "sph_pcisph_refine": (C.c_int, [_H, _i32p, _f32p]),
     "sph_implicit_viscosity_solve": (C.c_int, [_H, _i32p, _f32p]),
     "sph_synchronize": (C.c_int, [_H]),
+    "sph_set_stream": (C.c_int, [_H, C.c_void_p]),
+    "sph_profile_enable": (C.c_int, [_H, C.c_int32]),
+    "sph_profile_read": (C.c_int, [_H, C.POINTER(SphKernelStat), C.c_int32, _i32p]),
     "sph_slab_set_range": (C.c_int, [_H, C.c_int32, C.c_int32]),
     "sph_slab_info": (C.c_int, [_H, C.POINTER(SphSlabInfo)]),
     "sph_slab_begin_exchange": (C.c_int, [_H, _i32p]),
@@ -369,6 +376,20 @@ class Engine:
 
     def synchronize(self):
         self._check(self.lib.sph_synchronize(self._h))
+
+    def set_stream(self, cuda_stream: int):
+        """Run on the caller's stream (e.g. torch.cuda.current_stream().cuda_stream); 0 restores."""
+        self._check(self.lib.sph_set_stream(self._h, C.c_void_p(cuda_stream or None)))
+
+    def profile_enable(self, on: bool = True):
+        self._check(self.lib.sph_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """{kernel name: (launches, total device ms)} since the last read."""
+        rows = (SphKernelStat * 128)()
+        count = C.c_int32()
+        self._check(self.lib.sph_profile_read(self._h, rows, 128, C.byref(count)))
+        return {rows[i].name.decode(): (rows[i].launches, rows[i].total_ms) for i in range(count.value)}
 
     # -- slabs --
     def slab_set_range(self, z_lo: int, z_hi: int):

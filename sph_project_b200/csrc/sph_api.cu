@@ -327,6 +327,19 @@ FieldInfo field_info(int field) {
 
 }  // namespace
 
+int sph_prof_begin(SphHandle* h, const char* name) {
+    SphHandle::ProfRec r;
+    r.name = name;
+    for (cudaEvent_t* e : {&r.begin, &r.end}) {
+        if (!h->event_pool.empty()) { *e = h->event_pool.back(); h->event_pool.pop_back(); }
+        else if (cudaEventCreate(e) != cudaSuccess) return -1;
+    }
+    cudaEventRecord(r.begin, h->stream);
+    h->prof.push_back(r);
+    return (int)h->prof.size() - 1;
+}
+void sph_prof_end(SphHandle* h, int idx) { cudaEventRecord(h->prof[idx].end, h->stream); }
+
 extern "C" {
 
 int sph_abi_version(void) { return SPH_ABI_VERSION; }
@@ -358,6 +371,7 @@ int sph_create(const SphParams* p, SphHandle** out) {
     refresh_consts(h);
     int rc = SPH_OK;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SPH_E_CUDA; }
+    h->own_stream = h->stream;
     const size_t n = (size_t)c.cap;
 #define ALLOC(ptr, count) if (!rc) rc = dev_alloc(h, ptr, count)
     ALLOC(d.pv, n); ALLOC(d.pv_alt, n); ALLOC(d.vm, n); ALLOC(d.vm_alt, n);
@@ -405,7 +419,9 @@ int sph_destroy(SphHandle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (void* p : h->allocations) cudaFree(p);
     if (h->h_red) cudaFreeHost(h->h_red);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    for (auto& r : h->prof) { cudaEventDestroy(r.begin); cudaEventDestroy(r.end); }
+    for (cudaEvent_t e : h->event_pool) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return SPH_OK;
 }
@@ -816,6 +832,48 @@ int sph_implicit_viscosity_solve(SphHandle* h, int32_t* it, float* e) {
     if (it) *it = i;
     if (e) *e = err;
     return rc;
+}
+
+int sph_set_stream(SphHandle* h, void* cuda_stream) {
+    if (!h) return SPH_E_INVALID;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return SPH_OK;
+}
+
+int sph_profile_enable(SphHandle* h, int32_t enable) {
+    if (!h) return SPH_E_INVALID;
+    h->profiling = enable != 0;
+    return SPH_OK;
+}
+
+int sph_profile_read(SphHandle* h, SphKernelStat* out, int32_t capacity, int32_t* count) {
+    if (!h || !count) return SPH_E_INVALID;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int n = 0;
+    for (auto& r : h->prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.begin, r.end) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+        const char* name = r.name;
+        if (!strncmp(name, "(", 1)) name++;   // macro arguments may arrive parenthesised
+        int k = 0;
+        for (; k < n; k++) if (!strncmp(out[k].name, name, sizeof out[k].name - 1)) break;
+        if (k == n) {
+            if (n >= capacity || !out) { h->event_pool.push_back(r.begin); h->event_pool.push_back(r.end); continue; }
+            memset(&out[n], 0, sizeof out[n]);
+            strncpy(out[n].name, name, sizeof out[n].name - 1);
+            char* paren = strchr(out[n].name, ')');
+            if (paren) *paren = 0;
+            n++;
+        }
+        out[k].launches++;
+        out[k].total_ms += ms;
+        h->event_pool.push_back(r.begin);
+        h->event_pool.push_back(r.end);
+    }
+    h->prof.clear();
+    *count = n;
+    return SPH_OK;
 }
 
 // ---- Z-slab sharding: implemented in sph_slab.cu ------------------------------------------------

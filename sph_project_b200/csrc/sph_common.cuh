@@ -176,4 +176,24 @@ struct SphHandle {
     int64_t launches = 0;
     int scan_blocks_cap = 0;
     bool dyn_rigid_dirty = true;
+    // per-kernel event timing (sph_profile_enable / sph_profile_read)
+    cudaStream_t own_stream = nullptr;
+    bool profiling = false;
+    struct ProfRec { const char* name; cudaEvent_t begin, end; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+// brackets one kernel launch with CUDA events when profiling is on
+int sph_prof_begin(SphHandle* h, const char* name);
+void sph_prof_end(SphHandle* h, int idx);
+struct SphProf {
+    SphHandle* h;
+    int idx;
+    SphProf(SphHandle* handle, const char* name) : h(handle), idx(-1) {
+        if (h->profiling) idx = sph_prof_begin(h, name);
+    }
+    ~SphProf() {
+        if (idx >= 0) sph_prof_end(h, idx);
+    }
 };

@@ -158,9 +158,9 @@ void sph_exclusive_scan(SphHandle* h, const int* in, int n, int* out) {
         return;
     }
     const int tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, h->stream>>>(in, n, h->d.scan_tmp);
-    k_scan_sums<<<1, 1024, 0, h->stream>>>(h->d.scan_tmp, tiles);
-    k_scan_final<<<tiles, SCAN_THREADS, 0, h->stream>>>(in, n, h->d.scan_tmp, out);
+    { SphProf p(h, "k_scan_tile_sums"); k_scan_tile_sums<<<tiles, SCAN_THREADS, 0, h->stream>>>(in, n, h->d.scan_tmp); }
+    { SphProf p(h, "k_scan_sums"); k_scan_sums<<<1, 1024, 0, h->stream>>>(h->d.scan_tmp, tiles); }
+    { SphProf p(h, "k_scan_final"); k_scan_final<<<tiles, SCAN_THREADS, 0, h->stream>>>(in, n, h->d.scan_tmp, out); }
     h->launches += 3;
 }
 
@@ -174,14 +174,15 @@ int sph_sort_particles(SphHandle* h) {
     cudaMemsetAsync(d.cell_count, 0, sizeof(int) * (size_t)c.ncell, st);
     const int nb = (c.N + SPH_BLOCK - 1) / SPH_BLOCK;
     if (c.N > 0) {
+        SphProf p(h, "k_cell_index");
         k_cell_index<<<nb, SPH_BLOCK, 0, st>>>(c, d);
         h->launches++;
     }
     sph_exclusive_scan(h, d.cell_count, c.ncell, d.cell_start);
     if (c.N > 0) {
-        k_scatter_perm<<<nb, SPH_BLOCK, 0, st>>>(c, d);
-        k_sort_cells<<<(c.ncell + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, st>>>(c, d);
-        k_gather<<<nb, SPH_BLOCK, 0, st>>>(c, d, (h->P.flags & SPH_FLAG_SLAB) ? 1 : 0);
+        { SphProf p(h, "k_scatter_perm"); k_scatter_perm<<<nb, SPH_BLOCK, 0, st>>>(c, d); }
+        { SphProf p(h, "k_sort_cells"); k_sort_cells<<<(c.ncell + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, st>>>(c, d); }
+        { SphProf p(h, "k_gather"); k_gather<<<nb, SPH_BLOCK, 0, st>>>(c, d, (h->P.flags & SPH_FLAG_SLAB) ? 1 : 0); }
         h->launches += 3;
         swap_ptr(d.pv, d.pv_alt);
         swap_ptr(d.vm, d.vm_alt);

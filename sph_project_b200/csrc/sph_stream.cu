@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_ref_cell_hist(Consts c, Dev d, in
 #define LAUNCH_N(kernel, n, ...)                                                  \
     do {                                                                          \
         if ((n) > 0) {                                                            \
+            SphProf _prof(h, #kernel);                                            \
             kernel<<<GRID(n), SPH_BLOCK, 0, h->stream>>>(__VA_ARGS__);            \
             h->launches++;                                                        \
         }                                                                         \

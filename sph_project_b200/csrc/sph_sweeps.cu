@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_neighbor_fill(Consts c, Dev d, co
 #define LAUNCH(kernel)                                                        \
     do {                                                                      \
         if (h->c.N > 0) {                                                     \
+            SphProf _prof(h, #kernel);                                        \
             kernel<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d); \
             h->launches++;                                                    \
         }                                                                     \
@@ -345,6 +346,7 @@ void sph_launch_cg_Ap(SphHandle* h) { LAUNCH(k_cg_Ap); }
 
 void sph_launch_neighbor_count(SphHandle* h, int* counts) {
     if (h->c.N <= 0) return;
+    SphProf _prof(h, "k_neighbor_count");
     k_neighbor_count<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d, counts);
     h->launches++;
 }
