@@ -38,11 +38,28 @@ UNIT = "particle-steps/s"
 
 # compulsory bytes per particle per launch; rows = all particles (fluid + boundary)
 ALGO_BYTES = {
-    "k_density": 24, "k_dfsph_alpha": 24, "k_dfsph_density_change<false>": 36, "k_dfsph_density_change<true>": 40,
-    "k_dfsph_correct<true>": 52, "k_dfsph_correct<false>": 52, "k_surface_tension": 44, "k_viscosity": 64,
-    "k_pressure_accel<false>": 48, "k_pressure_accel<true>": 48, "k_rigid_volume": 24, "k_gather": 156,
-    "k_cell_index": 20, "k_update_velocity": 36, "k_update_position": 36, "k_boundary": 32,
+    "k_density": 24, "k_dfsph_alpha": 24, "k_dfsph_density_change": 40, "k_dfsph_correct": 52, "k_surface_tension": 44,
+    "k_viscosity": 64, "k_pressure_accel": 48, "k_rigid_volume": 24, "k_gather": 156, "k_cell_index": 20,
+    "k_update_velocity": 36, "k_update_position": 36, "k_boundary": 32,
 }
+LIST_CONSUMERS = ("k_dfsph_alpha", "k_dfsph_density_change", "k_dfsph_correct", "k_surface_tension", "k_viscosity",
+                  "k_pressure_accel")
+
+
+def algo_bytes(kernel, n_total, n_pairs):
+    """Algorithmic bytes of one launch: the SURVEY 8(d) per-particle figure x all particles, plus the
+    neighbour list itself (4 B per accepted pair) for the kernel that writes it (k_density<.., true>)
+    and for the kernels that stream it instead of re-deriving it from positions."""
+    base = kernel.split("<")[0]
+    if base not in ALGO_BYTES:
+        return None
+    b = ALGO_BYTES[base] * n_total
+    args = kernel.replace(" ", "")
+    if base == "k_density" and args.endswith(",true>"):
+        b += 4 * n_pairs + 4 * n_total
+    if base in LIST_CONSUMERS and args.endswith("true>") and not (base == "k_dfsph_density_change" and args.endswith(",false,true>")):
+        b += 4 * n_pairs
+    return b
 
 
 def dam_break_scene(method="dfsph", scale=1.0, n_slabs=1):
@@ -278,16 +295,21 @@ def run_gpu(args, rank, world, local_rank):
     prof_ms = evp0.elapsed_time(evp1)
     total_kernel_ms = sum(v[1] for v in prof.values())
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])
-    kernels = [{"name": k, "launches": int(v[0]), "ms_per_launch": v[1] / v[0], "share": v[1] / total_kernel_ms,
-                "algo_GBps": (ALGO_BYTES[k] * n_total / (v[1] / v[0] * 1e-3) / 1e9) if k in ALGO_BYTES else None}
-               for k, v in top[:8]]
+    from sph_project_b200._native import F as _F
+    mat_now = container.particle_materials.to_numpy(n_total)
+    n_pairs = int(eng.get_field(_F.NEIGHBOR_COUNT, n_total)[mat_now == 1].sum())
+    kernels = []
+    for k, v in top[:10]:
+        ab = algo_bytes(k, n_total, n_pairs)
+        kernels.append({"name": k, "launches": int(v[0]), "ms_per_launch": v[1] / v[0], "share": v[1] / total_kernel_ms,
+                        "algo_GBps": (ab / (v[1] / v[0] * 1e-3) / 1e9) if ab else None})
     dom_name, (dom_launches, dom_ms) = top[0]
-    dom_bytes = ALGO_BYTES.get(dom_name, 0) * n_total
+    dom_bytes = algo_bytes(dom_name, n_total, n_pairs) or 0
     achieved = dom_bytes / (dom_ms / dom_launches * 1e-3) / 1e9
     roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms / dom_launches,
-                "share_of_kernel_time": dom_ms / total_kernel_ms,
+                "share_of_kernel_time": dom_ms / total_kernel_ms, "accepted_pairs": n_pairs,
                 "note": "neighbour sweeps are FP32-issue / L1-bound, not HBM-bound (SURVEY.md 8(d)); frac is the compulsory-bytes figure",
                 "profiled_pass_ms_per_step": prof_ms / args.steps, "kernels": kernels}
 

@@ -4,6 +4,7 @@
 // runtime's message in sph_last_error().
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sph_kernels.h"
@@ -131,13 +132,13 @@ int dfsph_correct_divergence_error(SphHandle* h, int* iters, float* err) {
     const Consts& c = h->c;
     int it = 0, rc;
     float e = 0.f;
-    sph_launch_dfsph_density_derivative(h);
+    // density derivative, kappa_v and the error sum are one fused kernel here (same arithmetic as
+    // the three upstream kernels; sph_run_task exposes them separately)
+    sph_launch_dfsph_density_derivative(h, true);
     while (it < 1 || it < 1000) {
-        sph_launch_dfsph_kappa_v(h);
         sph_launch_dfsph_correct_divergence(h);
-        sph_launch_dfsph_density_derivative(h);
         if ((rc = zero_red(h, RED_ERR))) return rc;
-        sph_launch_dfsph_divergence_error(h);
+        sph_launch_dfsph_density_derivative(h, true);
         if ((rc = read_red(h))) return rc;   // the reference's per-iteration device->host read
         e = (float)h->h_red[RED_ERR] / (float)c.N;
         const float eta = 0.001f * c.rho0 / c.dt;
@@ -153,13 +154,11 @@ int dfsph_correct_density_error(SphHandle* h, int* iters, float* err) {
     const Consts& c = h->c;
     int it = 0, rc;
     float e = 0.f;
-    sph_launch_dfsph_density_star(h);
+    sph_launch_dfsph_density_star(h, true);
     while (it < 1 || it < 1000) {
-        sph_launch_dfsph_kappa(h);
         sph_launch_dfsph_correct_density(h);
-        sph_launch_dfsph_density_star(h);
         if ((rc = zero_red(h, RED_ERR))) return rc;
-        sph_launch_dfsph_density_error(h);
+        sph_launch_dfsph_density_star(h, true);
         if ((rc = read_red(h))) return rc;
         e = (float)h->h_red[RED_ERR] / (float)c.N;
         it++;
@@ -396,6 +395,16 @@ int sph_create(const SphParams* p, SphHandle** out) {
     ALLOC(d.object_material, SPH_MAX_OBJECTS); ALLOC(d.rigid_is_dynamic, SPH_MAX_OBJECTS);
     ALLOC(d.rigid_state, SPH_MAX_OBJECTS * 24); ALLOC(d.rigid_wrench, SPH_MAX_OBJECTS * 6);
     ALLOC(d.red, RED_COUNT);
+    {   // neighbour lists: ELL, nbr_kmax slots x stride (SPH_B200_KMAX / SPH_B200_NO_LISTS override)
+        const char* e = getenv("SPH_B200_NO_LISTS");
+        h->lists_enabled = !(e && e[0] == '1');
+        const char* k = getenv("SPH_B200_KMAX");
+        d.nbr_kmax = k ? atoi(k) : 96;
+        if (d.nbr_kmax < 1) d.nbr_kmax = 1;
+        d.nbr_stride = (int)((n + 31) / 32 * 32);
+        if (h->lists_enabled) { ALLOC(d.nbr, (size_t)d.nbr_kmax * (size_t)d.nbr_stride); }
+        ALLOC(d.nbr_count, n);
+    }
     if (!rc) {
         h->staging_bytes = (n ? n : 1) * 36;
         float* st = nullptr;
@@ -465,6 +474,7 @@ int sph_add_particles(SphHandle* h, int32_t object_id, int32_t n, const float* x
     CUDA_TRY(h, cudaStreamSynchronize(st));   // host vectors go out of scope
     c.N += n;
     h->sorted_valid = false;
+    h->list_valid = false;
     h->dyn_rigid_dirty = true;
     return SPH_OK;
 }
@@ -510,6 +520,7 @@ int sph_set_field(SphHandle* h, int32_t field, const void* src, size_t bytes) {
     if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (field == SPH_F_POSITION) h->sorted_valid = false;
+    if (field == SPH_F_POSITION || field == SPH_F_MATERIAL) h->list_valid = false;
     if (field == SPH_F_MATERIAL || field == SPH_F_IS_DYNAMIC) h->dyn_rigid_dirty = true;
     return SPH_OK;
 }
@@ -527,6 +538,7 @@ int sph_fill_field(SphHandle* h, int32_t field, double value) {
     int comps = sph_staging_to_field(h, field, (int)n);
     if (comps < 0) return fail(h, comps, "field not available for this solver");
     if (field == SPH_F_MATERIAL || field == SPH_F_IS_DYNAMIC) h->dyn_rigid_dirty = true;
+    if (field == SPH_F_POSITION || field == SPH_F_MATERIAL) h->list_valid = false;
     return last_launch(h);
 }
 
@@ -594,7 +606,7 @@ int sph_set_scalar(SphHandle* h, int32_t s, double v) {
         case SPH_S_DT: h->P.dt = v; refresh_consts(h); break;
         case SPH_S_PARTICLE_NUM:
             if (v < 0 || v > h->c.cap) return fail(h, SPH_E_CAPACITY, "particle_num out of range");
-            h->c.N = (int)v; h->sorted_valid = false; break;
+            h->c.N = (int)v; h->sorted_valid = false; h->list_valid = false; break;
         case SPH_S_FLUID_PARTICLE_NUM: h->Nfluid = (int)v; break;
         case SPH_S_PCISPH_K: h->c.pcisph_k = (float)v; break;
         case SPH_S_DENSITY_ERROR: h->density_error = (float)v; break;
@@ -753,8 +765,8 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
         case SPH_T_COPY_BACK_ORIGINAL_VELOCITY: sph_launch_cg_velocity_restore(h); break;
         case SPH_T_WCSPH_COMPUTE_PRESSURE: sph_launch_wcsph_pressure(h); break;
         case SPH_T_DFSPH_COMPUTE_ALPHA: sph_launch_dfsph_alpha(h); break;
-        case SPH_T_DFSPH_COMPUTE_DENSITY_DERIVATIVE: sph_launch_dfsph_density_derivative(h); break;
-        case SPH_T_DFSPH_COMPUTE_DENSITY_STAR: sph_launch_dfsph_density_star(h); break;
+        case SPH_T_DFSPH_COMPUTE_DENSITY_DERIVATIVE: sph_launch_dfsph_density_derivative(h, false); break;
+        case SPH_T_DFSPH_COMPUTE_DENSITY_STAR: sph_launch_dfsph_density_star(h, false); break;
         case SPH_T_DFSPH_COMPUTE_KAPPA_V: sph_launch_dfsph_kappa_v(h); break;
         case SPH_T_DFSPH_CORRECT_DIVERGENCE_STEP: sph_launch_dfsph_correct_divergence(h); break;
         case SPH_T_DFSPH_COMPUTE_DENSITY_DERIVATIVE_ERROR:

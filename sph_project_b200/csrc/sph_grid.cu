@@ -197,5 +197,6 @@ int sph_sort_particles(SphHandle* h) {
         swap_ptr(d.ghost_slot, d.ghost_slot_alt);
     }
     h->sorted_valid = true;
+    h->list_valid = false;
     return cudaGetLastError() == cudaSuccess ? SPH_OK : SPH_E_CUDA;
 }

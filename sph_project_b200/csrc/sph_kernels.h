@@ -45,8 +45,9 @@ void sph_launch_temp_pressure_accel(SphHandle* h);
 void sph_launch_surface_tension(SphHandle* h);
 void sph_launch_viscosity(SphHandle* h);
 void sph_launch_dfsph_alpha(SphHandle* h);
-void sph_launch_dfsph_density_derivative(SphHandle* h);
-void sph_launch_dfsph_density_star(SphHandle* h);
+void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused);   // fused: + kappa_v + error sum
+void sph_launch_dfsph_density_star(SphHandle* h, bool fused);         // fused: + kappa + error sum
+bool sph_lists_ready(SphHandle* h);
 void sph_launch_dfsph_correct_divergence(SphHandle* h);
 void sph_launch_dfsph_correct_density(SphHandle* h);
 void sph_launch_pcisph_density_star(SphHandle* h);

@@ -346,10 +346,10 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_ref_cell_hist(Consts c, Dev d, in
 
 void sph_launch_gravity(SphHandle* h) { LAUNCH_N(k_gravity, h->c.N, h->c, h->d); }
 void sph_launch_update_velocity(SphHandle* h) { LAUNCH_N(k_update_velocity, h->c.N, h->c, h->d); }
-void sph_launch_update_position(SphHandle* h) { LAUNCH_N(k_update_position, h->c.N, h->c, h->d); }
-void sph_launch_boundary(SphHandle* h, int t) { LAUNCH_N(k_boundary, h->c.N, h->c, h->d, t); }
-void sph_launch_renew_rigid(SphHandle* h) { LAUNCH_N(k_renew_rigid, h->c.N, h->c, h->d); }
-void sph_launch_prepare_emitter(SphHandle* h) { LAUNCH_N(k_prepare_emitter, h->c.N, h->c, h->d); }
+void sph_launch_update_position(SphHandle* h) { LAUNCH_N(k_update_position, h->c.N, h->c, h->d); h->list_valid = false; }
+void sph_launch_boundary(SphHandle* h, int t) { LAUNCH_N(k_boundary, h->c.N, h->c, h->d, t); h->list_valid = false; }
+void sph_launch_renew_rigid(SphHandle* h) { LAUNCH_N(k_renew_rigid, h->c.N, h->c, h->d); h->list_valid = false; }
+void sph_launch_prepare_emitter(SphHandle* h) { LAUNCH_N(k_prepare_emitter, h->c.N, h->c, h->d); h->list_valid = false; }
 void sph_launch_wcsph_pressure(SphHandle* h) { LAUNCH_N(k_wcsph_pressure, h->c.N, h->c, h->d); }
 void sph_launch_dfsph_kappa_v(SphHandle* h) { LAUNCH_N(k_dfsph_kappa_v, h->c.N, h->c, h->d); }
 void sph_launch_dfsph_kappa(SphHandle* h) { LAUNCH_N(k_dfsph_kappa, h->c.N, h->c, h->d); }

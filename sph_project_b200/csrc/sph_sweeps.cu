@@ -1,5 +1,12 @@
-// sph_sweeps.cu — per-particle neighbour summations ("sweeps"): one thread per particle walks the
-// 27-cell window of the cell-sorted SoA (9 contiguous runs) and accumulates the task's sum.
+// sph_sweeps.cu — per-particle neighbour summations ("sweeps"), one thread per particle.
+//
+// Positions are frozen between a sort and the next position update, and every solver runs many
+// sweeps in that interval (DFSPH: density, alpha, the whole divergence solve, then next step's
+// surface tension, viscosity and the whole density solve).  So the first sweep after a sort
+// (compute_density) walks the 27-cell window of the cell-sorted SoA once, and records the accepted
+// neighbours of every fluid particle in an ELL list (nbr[k][i], coalesced along i).  All later
+// sweeps stream their list instead of re-testing ~250 candidates for ~40 hits.  LIST = false
+// instantiations walk the window directly (rigid rows, stale lists, list overflow).
 //
 // Each kernel replaces one @ti.kernel + its *_task of the reference (cited per kernel); the task
 // bodies are inlined C++ lambdas where upstream passes ti.template() callbacks into
@@ -21,7 +28,7 @@ __device__ __forceinline__ void add_wrench(const Dev& d, int obj, float3 force, 
     atomicAdd(w + 3, tq.x); atomicAdd(w + 4, tq.y); atomicAdd(w + 5, tq.z);
 }
 
-// compute_rigid_particle_volume (base_solver.py:105-123)
+// compute_rigid_particle_volume (base_solver.py:105-123); rigid rows, always a window walk
 __global__ void __launch_bounds__(SPH_BLOCK) k_rigid_volume(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
@@ -37,22 +44,47 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_rigid_volume(Consts c, Dev d) {
     reinterpret_cast<float*>(d.vm + i)[3] = c.rho0 * V;
 }
 
-// compute_density (base_solver.py:521-541)
+// compute_density (base_solver.py:521-541) fused with the neighbour-list build.
+// DENSITY: write rho; BUILD: record the accepted neighbours (walk order) and their count.
+template <bool DENSITY, bool BUILD>
 __global__ void __launch_bounds__(SPH_BLOCK) k_density(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
     float4 pi = d.pv[i];
-    if (!(pi.w > 0.0f)) return;
+    if (!(pi.w > 0.0f)) {
+        if (BUILD) d.nbr_count[i] = 0;
+        return;
+    }
     float ret = 0.0f;
-    for_all_neighbors(c, d, i, pi, [&](int, float4 pj, float3, float r2) {
-        ret += fabsf(pj.w) * kernel_W_q(c, sqrtf(r2) * c.inv_h);
+    int n = 0;
+    int* col = d.nbr + i;
+    const size_t stride = (size_t)d.nbr_stride;
+    const int kmax = d.nbr_kmax;
+    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3, float r2) {
+        if (DENSITY) ret += fabsf(pj.w) * kernel_W_q(c, sqrtf(r2) * c.inv_h);
+        if (BUILD) {
+            if (n < kmax) col[(size_t)n * stride] = j;
+            n++;
+        }
     });
-    d.rho[i] = (pi.w * c.kW + ret) * c.rho0;
+    if (DENSITY) d.rho[i] = (pi.w * c.kW + ret) * c.rho0;
+    if (BUILD) d.nbr_count[i] = n;   // may exceed kmax: such rows fall back to the window walk
+}
+
+// list rows whose count overflowed the list walk the window instead (same order, same result)
+template <bool LIST, class Visit>
+__device__ __forceinline__ void neighbors(const Consts& c, const Dev& d, int i, float4 pi, Visit&& visit) {
+    if (LIST) {
+        if (d.nbr_count[i] <= d.nbr_kmax) for_listed_neighbors(c, d, i, pi, visit);
+        else for_all_neighbors(c, d, i, pi, visit);
+    } else {
+        for_all_neighbors(c, d, i, pi, visit);
+    }
 }
 
 // compute_pressure_acceleration (base_solver.py:135-187) and, with TEMP, PCISPH's
 // compute_temp_pressure_acceleration (PCISPH.py:74-107: fluid rows, no rigid wrench, output a_p)
-template <bool TEMP>
+template <bool TEMP, bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_pressure_accel(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
@@ -67,7 +99,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_pressure_accel(Consts c, Dev d) {
     const float den_i = d.rho[i];
     const float dpi = d.p[i] / (den_i * den_i);
     float3 ret = make_float3(0.f, 0.f, 0.f);
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+    neighbors<LIST>(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
         const float gs = kernel_gradient_scale(c, r2);
         float coef;
         if (pj.w > 0.0f) {
@@ -87,6 +119,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_pressure_accel(Consts c, Dev d) {
 }
 
 // compute_surface_tension_acceleration (base_solver.py:209-229): a_i += sum
+template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_surface_tension(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
@@ -94,7 +127,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_surface_tension(Consts c, Dev d) 
     if (!(pi.w > 0.0f)) return;
     const float sm = c.sigma / mass_of(d, i);
     float3 a = make_float3(0.f, 0.f, 0.f);
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+    neighbors<LIST>(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
         if (!(pj.w > 0.0f)) return;
         const float w = r2 > c.diameter2 ? kernel_W_q(c, sqrtf(r2) * c.inv_h) : c.w_diameter;
         const float s = sm * mass_of(d, j) * w;
@@ -105,6 +138,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_surface_tension(Consts c, Dev d) 
 }
 
 // compute_viscosity_acceleration_standard (base_solver.py:231-278): a_i += sum / rho0
+template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_viscosity(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
@@ -113,7 +147,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_viscosity(Consts c, Dev d) {
     const float4 vi = d.vm[i];
     const float den_i = d.rho[i];
     float3 a = make_float3(0.f, 0.f, 0.f);
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+    neighbors<LIST>(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
         const float4 vj = __ldg(d.vm + j);
         const float v_xy = dot3(make_float3(vi.x - vj.x, vi.y - vj.y, vi.z - vj.z), R);
         const float gs = kernel_gradient_scale(c, r2);
@@ -135,6 +169,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_viscosity(Consts c, Dev d) {
 }
 
 // DFSPH compute_alpha (DFSPH.py:22-62)
+template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_alpha(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
@@ -142,7 +177,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_alpha(Consts c, Dev d) {
     if (!(pi.w > 0.0f)) return;
     float3 grad_i = make_float3(0.f, 0.f, 0.f);
     float sum_k = 0.0f;
-    for_all_neighbors(c, d, i, pi, [&](int, float4 pj, float3 R, float r2) {
+    neighbors<LIST>(c, d, i, pi, [&](int, float4 pj, float3 R, float r2) {
         const float s = -fabsf(pj.w) * kernel_gradient_scale(c, r2);
         const float3 g = R * s;
         if (pj.w > 0.0f) sum_k += dist2(g);
@@ -152,33 +187,49 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_alpha(Consts c, Dev d) {
     d.alpha[i] = sum_k > 1e-5f ? 1.0f / sum_k : 0.0f;
 }
 
-// DFSPH compute_density_derivative (DFSPH.py:65-101) / compute_density_star (:104-126)
-template <bool STAR>
+// DFSPH compute_density_derivative (DFSPH.py:65-101) / compute_density_star (:104-126).
+// FUSED (the library's own solver loops): also the kappa of the next correction step
+// (compute_kappa_v :132-137 / compute_kappa :217-223) and the error sum
+// (compute_density_derivative_error :205-211 / compute_density_error :285-294) into red[RED_ERR].
+template <bool STAR, bool LIST, bool FUSED>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
-    float4 pi = d.pv[i];
-    if (!(pi.w > 0.0f)) return;
-    const float4 vi = d.vm[i];
-    float delta = 0.0f;
-    int nn = 0;
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
-        const float4 vj = __ldg(d.vm + j);
-        const float vr = dot3(make_float3(vi.x - vj.x, vi.y - vj.y, vi.z - vj.z), R);
-        delta = fmaf(fabsf(pj.w) * kernel_gradient_scale(c, r2), vr, delta);
-        nn++;
-    });
-    if (STAR) {
-        d.rho_star[i] = fmaxf(d.rho[i] / c.rho0 + c.dt * delta, 1.0f);
-    } else {
-        float adv = fmaxf(delta, 0.0f);
-        if (nn < 20) adv = 0.0f;   // particle deficiency (DFSPH.py:93-95)
-        d.drho[i] = adv;
+    float err = 0.0f;
+    if (i < c.N) {
+        float4 pi = d.pv[i];
+        if (pi.w > 0.0f) {
+            const float4 vi = d.vm[i];
+            float delta = 0.0f;
+            int nn = 0;
+            neighbors<LIST>(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+                const float4 vj = __ldg(d.vm + j);
+                const float vr = dot3(make_float3(vi.x - vj.x, vi.y - vj.y, vi.z - vj.z), R);
+                delta = fmaf(fabsf(pj.w) * kernel_gradient_scale(c, r2), vr, delta);
+                nn++;
+            });
+            if (STAR) {
+                const float rs = fmaxf(d.rho[i] / c.rho0 + c.dt * delta, 1.0f);
+                d.rho_star[i] = rs;
+                if (FUSED) {
+                    d.kappa[i] = (rs - 1.0f) * d.alpha[i] * c.inv_dt;
+                    err = rs - 1.0f;
+                }
+            } else {
+                float adv = fmaxf(delta, 0.0f);
+                if (nn < 20) adv = 0.0f;   // particle deficiency (DFSPH.py:93-95)
+                d.drho[i] = adv;
+                if (FUSED) {
+                    d.kappa_v[i] = adv * d.alpha[i];
+                    err = c.rho0 * adv;
+                }
+            }
+        }
     }
+    if (FUSED) block_reduce_add(d.red + RED_ERR, (double)err);
 }
 
 // DFSPH correct_divergence_step (DFSPH.py:161-202) / correct_density_error_step (:245-283)
-template <bool DIVERGENCE>
+template <bool DIVERGENCE, bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_correct(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
@@ -191,7 +242,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_correct(Consts c, Dev d) {
     const float thresh = 1e-5f * c.dt;   // m_eps * dt
     const bool rigid_on = fabsf(k_i) > thresh;
     float3 dv = make_float3(0.f, 0.f, 0.f);
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+    neighbors<LIST>(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
         float s;
         if (pj.w > 0.0f) {
             const float k_j = __ldg(kappa + j);
@@ -212,7 +263,8 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_correct(Consts c, Dev d) {
 }
 
 // PCISPH compute_density_star (PCISPH.py:32-62): predicted positions, no self term, neighbour
-// set from the current positions.  Accumulates sum max(0, rho*/rho0 - 1) into red[0].
+// set from the current positions.  Accumulates sum max(0, rho*/rho0 - 1) into red[RED_ERR].
+template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_pcisph_density_star(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float err = 0.0f;
@@ -221,7 +273,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_pcisph_density_star(Consts c, Dev
         if (pi.w > 0.0f) {
             const float4 xi = d.x_pred[i];
             float ret = 0.0f;
-            for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3, float) {
+            neighbors<LIST>(c, d, i, pi, [&](int j, float4 pj, float3, float) {
                 float4 xj = pj.w > 0.0f ? __ldg(d.x_pred + j) : pj;
                 float r2 = dist2(make_float3(xi.x - xj.x, xi.y - xj.y, xi.z - xj.z));
                 ret += fabsf(pj.w) * kernel_W_q(c, sqrtf(r2) * c.inv_h);
@@ -230,7 +282,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_pcisph_density_star(Consts c, Dev
             err = fmaxf(0.0f, ret - 1.0f);
         }
     }
-    block_reduce_add(d.red + 0, (double)err);
+    block_reduce_add(d.red + RED_ERR, (double)err);
 }
 
 // implicit viscosity: A_ij = -c (grad W_ij (x) R) / (r^2 + 0.01 h^2)  (base_solver.py:348-371);
@@ -245,6 +297,7 @@ __device__ __forceinline__ float visc_A_scale(const Consts& c, const Dev& d, flo
 
 // prepare_conjugate_gradient_solver1, the per-particle part (base_solver.py:300-315):
 // D_i^-1, b_i and p_i <- x_i
+template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_cg_prepare1(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
@@ -255,7 +308,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_cg_prepare1(Consts c, Dev d) {
     // ret = -sum A_ij (symmetric in R (x) R): 6 unique entries
     float sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
     float3 b = make_float3(0.f, 0.f, 0.f);
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+    neighbors<LIST>(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
         const float a = -visc_A_scale(c, d, vi.w, den_i, j, pj, r2);   // ret -= A_ij
         sxx = fmaf(a * R.x, R.x, sxx); sxy = fmaf(a * R.x, R.y, sxy); sxz = fmaf(a * R.x, R.z, sxz);
         syy = fmaf(a * R.y, R.y, syy); syz = fmaf(a * R.y, R.z, syz); szz = fmaf(a * R.z, R.z, szz);
@@ -280,6 +333,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_cg_prepare1(Consts c, Dev d) {
 }
 
 // compute_Ap (base_solver.py:373-391): Ap_i = p_i + dt/rho0 * D_i^-1 sum_{fluid j} (-A_ij) p_j
+template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_cg_Ap(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
@@ -288,7 +342,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_cg_Ap(Consts c, Dev d) {
     const float mi = mass_of(d, i);
     const float den_i = d.rho[i];
     float3 s = make_float3(0.f, 0.f, 0.f);
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
+    neighbors<LIST>(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
         if (!(pj.w > 0.0f)) return;
         const float a = -visc_A_scale(c, d, mi, den_i, j, pj, r2);
         const float4 pj_cg = __ldg(d.cg_p + j);
@@ -320,29 +374,59 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_neighbor_fill(Consts c, Dev d, co
 
 }  // namespace
 
-#define LAUNCH(kernel)                                                        \
+#define LAUNCH(...)                                                           \
     do {                                                                      \
         if (h->c.N > 0) {                                                     \
-            SphProf _prof(h, #kernel);                                        \
-            kernel<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d); \
+            SphProf _prof(h, #__VA_ARGS__);                                   \
+            __VA_ARGS__<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d); \
             h->launches++;                                                    \
         }                                                                     \
     } while (0)
 
+// list-based instantiation when the neighbour lists are current, else the window walk
+#define LAUNCH_LIST(kernel, ...)                                              \
+    do {                                                                      \
+        if (sph_lists_ready(h)) LAUNCH(kernel<__VA_ARGS__ true>);             \
+        else LAUNCH(kernel<__VA_ARGS__ false>);                               \
+    } while (0)
+
+// (re)build the lists without touching densities when a list consumer finds them stale
+bool sph_lists_ready(SphHandle* h) {
+    if (!h->lists_enabled || !h->d.nbr) return false;
+    if (!h->list_valid) {
+        LAUNCH(k_density<false, true>);
+        h->list_valid = true;
+    }
+    return true;
+}
+
 void sph_launch_rigid_volume(SphHandle* h) { LAUNCH(k_rigid_volume); }
-void sph_launch_density(SphHandle* h) { LAUNCH(k_density); }
-void sph_launch_pressure_accel(SphHandle* h) { LAUNCH(k_pressure_accel<false>); }
-void sph_launch_temp_pressure_accel(SphHandle* h) { LAUNCH(k_pressure_accel<true>); }
-void sph_launch_surface_tension(SphHandle* h) { LAUNCH(k_surface_tension); }
-void sph_launch_viscosity(SphHandle* h) { LAUNCH(k_viscosity); }
-void sph_launch_dfsph_alpha(SphHandle* h) { LAUNCH(k_dfsph_alpha); }
-void sph_launch_dfsph_density_derivative(SphHandle* h) { LAUNCH(k_dfsph_density_change<false>); }
-void sph_launch_dfsph_density_star(SphHandle* h) { LAUNCH(k_dfsph_density_change<true>); }
-void sph_launch_dfsph_correct_divergence(SphHandle* h) { LAUNCH(k_dfsph_correct<true>); }
-void sph_launch_dfsph_correct_density(SphHandle* h) { LAUNCH(k_dfsph_correct<false>); }
-void sph_launch_pcisph_density_star(SphHandle* h) { LAUNCH(k_pcisph_density_star); }
-void sph_launch_cg_prepare1(SphHandle* h) { LAUNCH(k_cg_prepare1); }
-void sph_launch_cg_Ap(SphHandle* h) { LAUNCH(k_cg_Ap); }
+void sph_launch_density(SphHandle* h) {
+    if (h->lists_enabled && h->d.nbr) {
+        LAUNCH(k_density<true, true>);
+        h->list_valid = true;
+    } else {
+        LAUNCH(k_density<true, false>);
+    }
+}
+void sph_launch_pressure_accel(SphHandle* h) { LAUNCH_LIST(k_pressure_accel, false, ); }
+void sph_launch_temp_pressure_accel(SphHandle* h) { LAUNCH_LIST(k_pressure_accel, true, ); }
+void sph_launch_surface_tension(SphHandle* h) { LAUNCH_LIST(k_surface_tension, ); }
+void sph_launch_viscosity(SphHandle* h) { LAUNCH_LIST(k_viscosity, ); }
+void sph_launch_dfsph_alpha(SphHandle* h) { LAUNCH_LIST(k_dfsph_alpha, ); }
+void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused) {
+    if (sph_lists_ready(h)) { if (fused) LAUNCH(k_dfsph_density_change<false, true, true>); else LAUNCH(k_dfsph_density_change<false, true, false>); }
+    else { if (fused) LAUNCH(k_dfsph_density_change<false, false, true>); else LAUNCH(k_dfsph_density_change<false, false, false>); }
+}
+void sph_launch_dfsph_density_star(SphHandle* h, bool fused) {
+    if (sph_lists_ready(h)) { if (fused) LAUNCH(k_dfsph_density_change<true, true, true>); else LAUNCH(k_dfsph_density_change<true, true, false>); }
+    else { if (fused) LAUNCH(k_dfsph_density_change<true, false, true>); else LAUNCH(k_dfsph_density_change<true, false, false>); }
+}
+void sph_launch_dfsph_correct_divergence(SphHandle* h) { LAUNCH_LIST(k_dfsph_correct, true, ); }
+void sph_launch_dfsph_correct_density(SphHandle* h) { LAUNCH_LIST(k_dfsph_correct, false, ); }
+void sph_launch_pcisph_density_star(SphHandle* h) { LAUNCH_LIST(k_pcisph_density_star, ); }
+void sph_launch_cg_prepare1(SphHandle* h) { LAUNCH_LIST(k_cg_prepare1, ); }
+void sph_launch_cg_Ap(SphHandle* h) { LAUNCH_LIST(k_cg_Ap, ); }
 
 void sph_launch_neighbor_count(SphHandle* h, int* counts) {
     if (h->c.N <= 0) return;
