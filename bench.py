@@ -339,11 +339,17 @@ def run_gpu(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         lib = oracle_library()
-        c2, s2 = make_sim(dam_break_scene("dfsph", scale=0.5), lib)
-        v, dt, st2 = time_cpu(s2, c2, 4, 1)
+        c2, s2 = make_sim(dam_break_scene("dfsph"), lib)
+        s2.step(1)
+        t0 = time.perf_counter()
+        s2.step(1)
+        one = time.perf_counter() - t0
+        k = int(min(max(12.0 / max(one, 1e-3), 2), 40))      # about 12 s of CPU work
+        v, dt, st2 = time_cpu(s2, c2, k, 0)
         cpu = {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port", "cpu": cpu_model(),
-               "sample": f"half-scale geometry ({c2.fluid_particle_num[None]} fluid + {c2.particle_num[None] - c2.fluid_particle_num[None]} boundary), "
-                         f"4 steps after 1 warm-up from the initial lattice ({dt:.1f} s of CPU work)"}
+               "sample": f"full workload ({c2.fluid_particle_num[None]} fluid + {c2.particle_num[None] - c2.fluid_particle_num[None]} boundary), "
+                         f"{k} steps after 2 warm-up steps from the initial lattice, early window ({dt:.1f} s of CPU work, "
+                         f"{st2.total_dfsph_iterations / k:.1f}+{st2.total_dfsph_iterations_v / k:.1f} solver iterations/step)"}
 
     if rank == 0:
         line = {
