@@ -136,7 +136,7 @@ int dfsph_correct_divergence_error(SphHandle* h, int* iters, float* err) {
     // the three upstream kernels; sph_run_task exposes them separately)
     sph_launch_dfsph_density_derivative(h, true);
     while (it < 1 || it < 1000) {
-        sph_launch_dfsph_correct_divergence(h);
+        sph_launch_dfsph_correct_divergence(h, true);
         if ((rc = zero_red(h, RED_ERR))) return rc;
         sph_launch_dfsph_density_derivative(h, true);
         if ((rc = read_red(h))) return rc;   // the reference's per-iteration device->host read
@@ -156,7 +156,7 @@ int dfsph_correct_density_error(SphHandle* h, int* iters, float* err) {
     float e = 0.f;
     sph_launch_dfsph_density_star(h, true);
     while (it < 1 || it < 1000) {
-        sph_launch_dfsph_correct_density(h);
+        sph_launch_dfsph_correct_density(h, true);
         if ((rc = zero_red(h, RED_ERR))) return rc;
         sph_launch_dfsph_density_star(h, true);
         if ((rc = read_red(h))) return rc;
@@ -218,12 +218,12 @@ int implicit_viscosity_solve(SphHandle* h, int* iters, float* err) {
     int rc;
     sph_launch_cg_prepare1_pre(h);
     sph_launch_cg_prepare1(h);
-    sph_launch_cg_Ap(h);
+    sph_launch_cg_Ap(h, true);
     sph_launch_cg_prepare2(h);
     float tol = 1000.0f;
     int it = 0;
     while (tol > 1e-6f && it < 1000) {
-        sph_launch_cg_Ap(h);
+        sph_launch_cg_Ap(h, true);
         if ((rc = cg_dots(h))) return rc;
         sph_launch_cg_update_x(h);
         if ((rc = cg_update_r(h))) return rc;
@@ -232,7 +232,7 @@ int implicit_viscosity_solve(SphHandle* h, int* iters, float* err) {
         it++;
     }
     sph_launch_cg_velocity_from_x(h);
-    sph_launch_viscosity(h);
+    sph_launch_viscosity(h, true);
     sph_launch_cg_velocity_restore(h);
     sph_launch_cg_prepare_guess(h);
     *iters = it; *err = tol;
@@ -244,7 +244,7 @@ int non_pressure_acceleration(SphHandle* h, SphStepStats* st) {
     sph_launch_gravity(h);
     sph_launch_surface_tension(h);
     if (h->P.visc_method == SPH_VISC_STANDARD) {
-        sph_launch_viscosity(h);
+        sph_launch_viscosity(h, true);   // surface tension just prepared aux
     } else {
         int it; float e;
         int rc = implicit_viscosity_solve(h, &it, &e);
@@ -402,8 +402,15 @@ int sph_create(const SphParams* p, SphHandle** out) {
         d.nbr_kmax = k ? atoi(k) : 96;
         if (d.nbr_kmax < 1) d.nbr_kmax = 1;
         d.nbr_stride = (int)((n + 31) / 32 * 32);
-        if (h->lists_enabled) { ALLOC(d.nbr, (size_t)d.nbr_kmax * (size_t)d.nbr_stride); }
+        if (h->lists_enabled) { ALLOC(d.nbr16, (size_t)d.nbr_kmax * (size_t)d.nbr_stride); }
         ALLOC(d.nbr_count, n);
+        ALLOC(d.chunk_desc, (n / SPH_BLOCK + 2) * 40);
+        ALLOC(d.win_stats, 4);
+        ALLOC(d.aux, n);
+        const char* w = getenv("SPH_B200_WMAX");   // window slots per CTA (16 B x payload arrays each)
+        h->wmax = w ? atoi(w) : 1536;
+        if (h->wmax < 64) h->wmax = 64;
+        if (h->wmax > 4096) h->wmax = 4096;
     }
     if (!rc) {
         h->staging_bytes = (n ? n : 1) * 36;
@@ -736,6 +743,18 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
     int rc = update_dynamic_rigid_flag(h);
     if (rc) return rc;
     const bool implicit = h->P.visc_method == SPH_VISC_IMPLICIT;
+    switch (task) {   // neighbour sweeps read the chunk windows laid out by the last sort
+        case SPH_T_COMPUTE_PRESSURE_ACCELERATION: case SPH_T_COMPUTE_SURFACE_TENSION_ACCELERATION:
+        case SPH_T_COMPUTE_VISCOSITY_ACCELERATION_STANDARD: case SPH_T_COMPUTE_DENSITY: case SPH_T_CG_PREPARE1:
+        case SPH_T_CG_COMPUTE_AP: case SPH_T_DFSPH_COMPUTE_ALPHA: case SPH_T_DFSPH_COMPUTE_DENSITY_DERIVATIVE:
+        case SPH_T_DFSPH_COMPUTE_DENSITY_STAR: case SPH_T_DFSPH_CORRECT_DIVERGENCE_STEP:
+        case SPH_T_DFSPH_CORRECT_DENSITY_ERROR_STEP: case SPH_T_PCISPH_COMPUTE_DENSITY_STAR:
+        case SPH_T_PCISPH_COMPUTE_TEMP_PRESSURE_ACCELERATION:
+            if (!h->sorted_valid)
+                return fail(h, SPH_E_STATE, "particles were added or moved by the host since the last sort: call prepare_neighborhood_search() first");
+            break;
+        default: break;
+    }
     if (task >= SPH_T_CG_PREPARE1 && task <= SPH_T_COPY_BACK_ORIGINAL_VELOCITY && !implicit)
         return fail(h, SPH_E_STATE, "implicit-viscosity kernels need viscosityMethod = implicit");
     switch (task) {
@@ -743,7 +762,7 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
         case SPH_T_COMPUTE_PRESSURE_ACCELERATION: sph_launch_pressure_accel(h); break;
         case SPH_T_COMPUTE_GRAVITY_ACCELERATION: sph_launch_gravity(h); break;
         case SPH_T_COMPUTE_SURFACE_TENSION_ACCELERATION: sph_launch_surface_tension(h); break;
-        case SPH_T_COMPUTE_VISCOSITY_ACCELERATION_STANDARD: sph_launch_viscosity(h); break;
+        case SPH_T_COMPUTE_VISCOSITY_ACCELERATION_STANDARD: sph_launch_viscosity(h, false); break;
         case SPH_T_COMPUTE_DENSITY: sph_launch_density(h); break;
         case SPH_T_ENFORCE_DOMAIN_BOUNDARY_3D: sph_launch_boundary(h, iarg); break;
         case SPH_T_RENEW_RIGID_PARTICLE_STATE: sph_launch_renew_rigid(h); break;
@@ -755,7 +774,7 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
         case SPH_T_INIT_RIGID_BODY_FORCE_AND_TORQUE: return sph_zero_rigid_wrench(h);
         case SPH_T_CG_PREPARE1: sph_launch_cg_prepare1_pre(h); sph_launch_cg_prepare1(h); break;
         case SPH_T_CG_PREPARE2: sph_launch_cg_prepare2(h); break;
-        case SPH_T_CG_COMPUTE_AP: sph_launch_cg_Ap(h); break;
+        case SPH_T_CG_COMPUTE_AP: sph_launch_cg_Ap(h, false); break;
         case SPH_T_CG_COMPUTE_ALPHA: if ((rc = cg_dots(h))) return rc; break;
         case SPH_T_CG_UPDATE_X: sph_launch_cg_update_x(h); break;
         case SPH_T_CG_UPDATE_R_AND_BETA: if ((rc = cg_update_r(h))) return rc; if (out) *out = h->cg_error; break;
@@ -768,7 +787,7 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
         case SPH_T_DFSPH_COMPUTE_DENSITY_DERIVATIVE: sph_launch_dfsph_density_derivative(h, false); break;
         case SPH_T_DFSPH_COMPUTE_DENSITY_STAR: sph_launch_dfsph_density_star(h, false); break;
         case SPH_T_DFSPH_COMPUTE_KAPPA_V: sph_launch_dfsph_kappa_v(h); break;
-        case SPH_T_DFSPH_CORRECT_DIVERGENCE_STEP: sph_launch_dfsph_correct_divergence(h); break;
+        case SPH_T_DFSPH_CORRECT_DIVERGENCE_STEP: sph_launch_dfsph_correct_divergence(h, false); break;
         case SPH_T_DFSPH_COMPUTE_DENSITY_DERIVATIVE_ERROR:
         case SPH_T_DFSPH_COMPUTE_DENSITY_ERROR:
             if ((rc = zero_red(h, RED_ERR))) return rc;
@@ -778,7 +797,7 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
             if (out) *out = (float)h->h_red[RED_ERR] / (float)h->c.N;
             break;
         case SPH_T_DFSPH_COMPUTE_KAPPA: sph_launch_dfsph_kappa(h); break;
-        case SPH_T_DFSPH_CORRECT_DENSITY_ERROR_STEP: sph_launch_dfsph_correct_density(h); break;
+        case SPH_T_DFSPH_CORRECT_DENSITY_ERROR_STEP: sph_launch_dfsph_correct_density(h, false); break;
         case SPH_T_PCISPH_COMPUTE_PREDICTED_VELOCITY: sph_launch_pcisph_predict_velocity(h); break;
         case SPH_T_PCISPH_COMPUTE_PREDICTED_POSITION: sph_launch_pcisph_predict_position(h); break;
         case SPH_T_PCISPH_COMPUTE_DENSITY_STAR:

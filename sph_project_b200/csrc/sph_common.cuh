@@ -75,12 +75,17 @@ struct Dev {
     // reductions
     double* red;              // small scratch for block reductions [64]
     // per-particle neighbour lists, valid while positions are frozen (sort .. next position update):
-    // nbr[k * nbr_stride + i] = k-th neighbour of fluid particle i, nbr_count[i] entries, walk order
-    int* nbr;
+    // nbr16[k * nbr_stride + i] = window slot (sph_window.cuh) of the k-th neighbour of fluid particle
+    // i, nbr_count[i] entries (rows with more than nbr_kmax re-derive their neighbours), walk order
+    unsigned short* nbr16;
     int* nbr_count;
-    int* nbr_overflow;        // set when some particle has more than nbr_kmax neighbours
     int nbr_stride;
     int nbr_kmax;
+    int* chunk_desc;          // SPH_DESC_INTS per chunk of SPH_BLOCK sorted particles
+    int* win_stats;           // [0] max window entries over chunks, [1] chunks above the smem budget
+    // aux[i] = (s0, s1, rho_i, m_i): per-sweep neighbour payload staged next to pv
+    //   DFSPH correction: (kappa, kappa / rho)   pressure: (p / rho^2, p)
+    float4* aux;
 };
 
 // ---- small vector helpers -------------------------------------------------------------------
@@ -158,39 +163,6 @@ __device__ __forceinline__ void for_all_neighbors(const Consts& c, const Dev& d,
     }
 }
 
-// The same neighbour set read back from the per-particle list built at the last density pass, in
-// the same (walk) order, so list-based sums are bit-identical to window walks.  Indices stream in
-// coalesced (lanes read consecutive i at one k); positions are gathered through L1/L2.
-template <class Visit>
-__device__ __forceinline__ void for_listed_neighbors(const Consts& c, const Dev& d, int i, float4 pi, Visit&& visit) {
-    const int n = d.nbr_count[i];
-    const int* __restrict__ col = d.nbr + i;
-    const size_t stride = (size_t)d.nbr_stride;
-    int k = 0;
-    for (; k + 4 <= n; k += 4) {   // 4 independent index -> position load chains in flight
-        const int j0 = __ldg(col + (size_t)k * stride), j1 = __ldg(col + (size_t)(k + 1) * stride);
-        const int j2 = __ldg(col + (size_t)(k + 2) * stride), j3 = __ldg(col + (size_t)(k + 3) * stride);
-        const float4 p0 = __ldg(d.pv + j0), p1 = __ldg(d.pv + j1), p2 = __ldg(d.pv + j2), p3 = __ldg(d.pv + j3);
-        float3 R;
-        R = make_float3(pi.x - p0.x, pi.y - p0.y, pi.z - p0.z); visit(j0, p0, R, dist2(R));
-        R = make_float3(pi.x - p1.x, pi.y - p1.y, pi.z - p1.z); visit(j1, p1, R, dist2(R));
-        R = make_float3(pi.x - p2.x, pi.y - p2.y, pi.z - p2.z); visit(j2, p2, R, dist2(R));
-        R = make_float3(pi.x - p3.x, pi.y - p3.y, pi.z - p3.z); visit(j3, p3, R, dist2(R));
-    }
-    for (; k < n; k++) {
-        const int j = __ldg(col + (size_t)k * stride);
-        const float4 pj = __ldg(d.pv + j);
-        const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        visit(j, pj, R, dist2(R));
-    }
-}
-
-template <bool LIST, class Visit>
-__device__ __forceinline__ void walk_neighbors(const Consts& c, const Dev& d, int i, float4 pi, Visit&& visit) {
-    if (LIST) for_listed_neighbors(c, d, i, pi, visit);
-    else for_all_neighbors(c, d, i, pi, visit);
-}
-
 // ---- host-side handle -------------------------------------------------------------------------
 #include <string>
 #include <vector>
@@ -218,6 +190,7 @@ struct SphHandle {
     bool dyn_rigid_dirty = true;
     bool lists_enabled = true;   // SPH_B200_NO_LISTS=1 forces window walks (A/B testing)
     bool list_valid = false;     // nbr lists match the current positions and order
+    int wmax = 1536;             // shared-memory window budget (slots) of the sweep kernels
     // per-kernel event timing (sph_profile_enable / sph_profile_read)
     cudaStream_t own_stream = nullptr;
     bool profiling = false;

@@ -128,11 +128,16 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_sort_cells(Consts c, Dev d) {
     }
 }
 
+// One block = one chunk of the sweep kernels: also counts the chunk's fluid rows (descriptor [2]).
 __global__ void __launch_bounds__(SPH_BLOCK) k_gather(Consts c, Dev d, int with_ghost_slot) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = k < c.N ? d.perm[k] : 0;
+    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < c.N) pv = d.pv[i];
+    const int nfluid = __syncthreads_count(pv.w > 0.0f);
+    if (threadIdx.x == 0) d.chunk_desc[(size_t)blockIdx.x * 40 + 2] = nfluid;
     if (k >= c.N) return;
-    const int i = d.perm[k];
-    d.pv_alt[k] = d.pv[i];
+    d.pv_alt[k] = pv;
     d.vm_alt[k] = d.vm[i];
     d.x0_alt[3 * k + 0] = d.x0[3 * i + 0];
     d.x0_alt[3 * k + 1] = d.x0[3 * i + 1];
@@ -147,6 +152,54 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_gather(Consts c, Dev d, int with_
     d.grid_id_alt[k] = d.grid_id[i];
     d.uid_alt[k] = d.uid[i];
     if (with_ghost_slot) d.ghost_slot_alt[k] = d.ghost_slot[i];
+}
+
+// Window descriptor of every chunk (layout in sph_window.cuh): the <= 9 index ranges of the sorted
+// arrays that cover the 27-cell neighbourhoods of the chunk's particles, overlapping ranges merged.
+// Runs after the gather (reads the new grid ids); one thread per chunk.
+__global__ void __launch_bounds__(SPH_BLOCK) k_chunk_windows(Consts c, Dev d, int nchunks, int wmax) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= nchunks) return;
+    const int first = ch * SPH_BLOCK, last = min(first + SPH_BLOCK, c.N) - 1;
+    const int c0 = d.grid_id[first], c1 = d.grid_id[last];
+    int* desc = d.chunk_desc + (size_t)ch * 40;
+    int ncp = 0, total = 0;
+    int cur_g = 0, cur_e = 0, cur_s = 0;
+    for (int r = 0; r < 9; r++) {
+        const int off = ((r / 3 - 1) * c.ny + (r % 3 - 1)) * c.nx;   // (dz, dy) row offset
+        const int lo = max(c0 + off - 1, 0), hi = min(c1 + off + 1, c.ncell - 1);
+        int g = 0, e = 0;
+        if (lo <= hi) {
+            g = d.cell_start[lo];
+            e = d.cell_start[hi + 1];
+        }
+        if (e <= g) {   // empty range: never indexed
+            desc[4 + r] = 0;
+            desc[13 + r] = 0;
+            continue;
+        }
+        if (ncp > 0 && g <= cur_e) {   // overlaps / touches the current copy: extend it
+            desc[4 + r] = g;
+            desc[13 + r] = cur_s + (g - cur_g);
+            if (e > cur_e) {
+                total += e - cur_e;
+                cur_e = e;
+                desc[31 + ncp - 1] = cur_e - cur_g;
+            }
+        } else {
+            cur_g = g; cur_e = e; cur_s = total;
+            desc[22 + ncp] = g;
+            desc[31 + ncp] = e - g;
+            ncp++;
+            total += e - g;
+            desc[4 + r] = g;
+            desc[13 + r] = cur_s;
+        }
+    }
+    desc[0] = total;
+    desc[1] = ncp;
+    atomicMax(d.win_stats + 0, total);
+    if (total > wmax) atomicAdd(d.win_stats + 1, 1);
 }
 
 }  // namespace
@@ -195,6 +248,12 @@ int sph_sort_particles(SphHandle* h) {
         swap_ptr(d.grid_id, d.grid_id_alt);
         swap_ptr(d.uid, d.uid_alt);
         swap_ptr(d.ghost_slot, d.ghost_slot_alt);
+        cudaMemsetAsync(d.win_stats, 0, 2 * sizeof(int), st);
+        {
+            SphProf p(h, "k_chunk_windows");
+            k_chunk_windows<<<(nb + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, st>>>(c, d, nb, h->wmax);
+            h->launches++;
+        }
     }
     h->sorted_valid = true;
     h->list_valid = false;

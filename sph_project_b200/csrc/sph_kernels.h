@@ -43,16 +43,16 @@ void sph_launch_density(SphHandle* h);
 void sph_launch_pressure_accel(SphHandle* h);
 void sph_launch_temp_pressure_accel(SphHandle* h);
 void sph_launch_surface_tension(SphHandle* h);
-void sph_launch_viscosity(SphHandle* h);
+void sph_launch_viscosity(SphHandle* h, bool aux_ready);   // aux_ready: aux already holds (., ., rho, m)
 void sph_launch_dfsph_alpha(SphHandle* h);
 void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused);   // fused: + kappa_v + error sum
 void sph_launch_dfsph_density_star(SphHandle* h, bool fused);         // fused: + kappa + error sum
 bool sph_lists_ready(SphHandle* h);
-void sph_launch_dfsph_correct_divergence(SphHandle* h);
-void sph_launch_dfsph_correct_density(SphHandle* h);
+void sph_launch_dfsph_correct_divergence(SphHandle* h, bool aux_ready);   // aux_ready: fused kernel wrote kappa into aux
+void sph_launch_dfsph_correct_density(SphHandle* h, bool aux_ready);
 void sph_launch_pcisph_density_star(SphHandle* h);
 void sph_launch_cg_prepare1(SphHandle* h);
-void sph_launch_cg_Ap(SphHandle* h);
+void sph_launch_cg_Ap(SphHandle* h, bool aux_ready);
 void sph_launch_neighbor_count(SphHandle* h, int* counts);
 void sph_launch_neighbor_fill(SphHandle* h, const int* offsets, int* indices);
 
