@@ -48,7 +48,7 @@ LIST_CONSUMERS = ("k_dfsph_alpha", "k_dfsph_density_change", "k_dfsph_correct", 
 
 def algo_bytes(kernel, n_total, n_pairs):
     """Algorithmic bytes of one launch: the SURVEY 8(d) per-particle figure x all particles, plus the
-    neighbour list itself (2 B per accepted pair: 16-bit window slots) for the kernel that writes it (k_density<.., true>)
+    neighbour list itself (4 B per accepted pair) for the kernel that writes it (k_density<.., true>)
     and for the kernels that stream it instead of re-deriving it from positions."""
     base = kernel.split("<")[0]
     if base not in ALGO_BYTES:
@@ -56,9 +56,9 @@ def algo_bytes(kernel, n_total, n_pairs):
     b = ALGO_BYTES[base] * n_total
     args = kernel.replace(" ", "")
     if base == "k_density" and args.endswith(",true>"):
-        b += 2 * n_pairs + 4 * n_total
+        b += 4 * n_pairs + 4 * n_total
     if base in LIST_CONSUMERS and args.endswith("true>") and not (base == "k_dfsph_density_change" and args.endswith(",false,true>")):
-        b += 2 * n_pairs
+        b += 4 * n_pairs
     return b
 
 

@@ -402,11 +402,12 @@ int sph_create(const SphParams* p, SphHandle** out) {
         d.nbr_kmax = k ? atoi(k) : 96;
         if (d.nbr_kmax < 1) d.nbr_kmax = 1;
         d.nbr_stride = (int)((n + 31) / 32 * 32);
-        if (h->lists_enabled) { ALLOC(d.nbr16, (size_t)d.nbr_kmax * (size_t)d.nbr_stride); }
+        if (h->lists_enabled) { ALLOC(d.nbr, (size_t)d.nbr_kmax * (size_t)d.nbr_stride); }
         ALLOC(d.nbr_count, n);
         ALLOC(d.chunk_desc, (n / SPH_BLOCK + 2) * 40);
         ALLOC(d.win_stats, 4);
-        ALLOC(d.aux, n);
+        ALLOC(d.recA, n);
+        ALLOC(d.recB, n);
         const char* w = getenv("SPH_B200_WMAX");   // window slots per CTA (16 B x payload arrays each)
         h->wmax = w ? atoi(w) : 1536;
         if (h->wmax < 64) h->wmax = 64;
@@ -482,6 +483,7 @@ int sph_add_particles(SphHandle* h, int32_t object_id, int32_t n, const float* x
     c.N += n;
     h->sorted_valid = false;
     h->list_valid = false;
+    h->rec_pos_valid = h->rec_vel_valid = false;
     h->dyn_rigid_dirty = true;
     return SPH_OK;
 }
@@ -528,6 +530,8 @@ int sph_set_field(SphHandle* h, int32_t field, const void* src, size_t bytes) {
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (field == SPH_F_POSITION) h->sorted_valid = false;
     if (field == SPH_F_POSITION || field == SPH_F_MATERIAL) h->list_valid = false;
+    if (field == SPH_F_POSITION || field == SPH_F_MATERIAL || field == SPH_F_REST_VOLUME) h->rec_pos_valid = false;
+    if (field == SPH_F_VELOCITY || field == SPH_F_MASS) h->rec_vel_valid = false;
     if (field == SPH_F_MATERIAL || field == SPH_F_IS_DYNAMIC) h->dyn_rigid_dirty = true;
     return SPH_OK;
 }
@@ -546,6 +550,8 @@ int sph_fill_field(SphHandle* h, int32_t field, double value) {
     if (comps < 0) return fail(h, comps, "field not available for this solver");
     if (field == SPH_F_MATERIAL || field == SPH_F_IS_DYNAMIC) h->dyn_rigid_dirty = true;
     if (field == SPH_F_POSITION || field == SPH_F_MATERIAL) h->list_valid = false;
+    if (field == SPH_F_POSITION || field == SPH_F_MATERIAL || field == SPH_F_REST_VOLUME) h->rec_pos_valid = false;
+    if (field == SPH_F_VELOCITY || field == SPH_F_MASS) h->rec_vel_valid = false;
     return last_launch(h);
 }
 
@@ -613,7 +619,7 @@ int sph_set_scalar(SphHandle* h, int32_t s, double v) {
         case SPH_S_DT: h->P.dt = v; refresh_consts(h); break;
         case SPH_S_PARTICLE_NUM:
             if (v < 0 || v > h->c.cap) return fail(h, SPH_E_CAPACITY, "particle_num out of range");
-            h->c.N = (int)v; h->sorted_valid = false; h->list_valid = false; break;
+            h->c.N = (int)v; h->sorted_valid = false; h->list_valid = false; h->rec_pos_valid = h->rec_vel_valid = false; break;
         case SPH_S_FLUID_PARTICLE_NUM: h->Nfluid = (int)v; break;
         case SPH_S_PCISPH_K: h->c.pcisph_k = (float)v; break;
         case SPH_S_DENSITY_ERROR: h->density_error = (float)v; break;

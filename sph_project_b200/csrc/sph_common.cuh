@@ -41,6 +41,12 @@ struct Consts {
     int z_lo, z_hi;   // owned cell layers (whole grid unless the handle is a slab)
 };
 
+// 32-byte neighbour record: one 256-bit load (LDG.E.256, sm_100+) fetches everything a sweep needs
+// about neighbour j.  lo = pv (x, y, z, +-V); hi = the per-sweep payload.
+struct __align__(32) Rec {
+    float4 lo, hi;
+};
+
 // device pointers; `cur` selects the live half of the ping-pong buffers
 struct Dev {
     float4* pv;   float4* pv_alt;
@@ -75,18 +81,28 @@ struct Dev {
     // reductions
     double* red;              // small scratch for block reductions [64]
     // per-particle neighbour lists, valid while positions are frozen (sort .. next position update):
-    // nbr16[k * nbr_stride + i] = window slot (sph_window.cuh) of the k-th neighbour of fluid particle
-    // i, nbr_count[i] entries (rows with more than nbr_kmax re-derive their neighbours), walk order
-    unsigned short* nbr16;
+    // nbr[k * nbr_stride + i] = sorted index of the k-th neighbour of fluid particle i (coalesced along
+    // i), nbr_count[i] entries (rows with more than nbr_kmax re-derive their neighbours), walk order
+    int* nbr;
     int* nbr_count;
     int nbr_stride;
     int nbr_kmax;
-    int* chunk_desc;          // SPH_DESC_INTS per chunk of SPH_BLOCK sorted particles
+    int* chunk_desc;          // SPH_DESC_INTS per chunk of SPH_BLOCK sorted particles (list build)
     int* win_stats;           // [0] max window entries over chunks, [1] chunks above the smem budget
-    // aux[i] = (s0, s1, rho_i, m_i): per-sweep neighbour payload staged next to pv
-    //   DFSPH correction: (kappa, kappa / rho)   pressure: (p / rho^2, p)
-    float4* aux;
+    // neighbour records gathered by the list-based sweeps (copies of the canonical arrays):
+    //   recA[j] = {pv_j, vm_j}                    velocity sweeps (density change, viscosity, CG setup)
+    //   recB[j] = {pv_j, (s0, s1, rho_j, m_j)}    scalar sweeps; (s0, s1) = (kappa, kappa/rho) for the
+    //                                              DFSPH correction, (p/rho^2, p) for the pressure force
+    Rec* recA;
+    Rec* recB;
 };
+
+// one 256-bit read-only gather of a neighbour record
+__device__ __forceinline__ void ldg_rec(const Rec* p, float4& lo, float4& hi) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
+        : "l"(p));
+}
 
 // ---- small vector helpers -------------------------------------------------------------------
 __device__ __forceinline__ float3 f3(float4 a) { return make_float3(a.x, a.y, a.z); }
@@ -190,6 +206,8 @@ struct SphHandle {
     bool dyn_rigid_dirty = true;
     bool lists_enabled = true;   // SPH_B200_NO_LISTS=1 forces window walks (A/B testing)
     bool list_valid = false;     // nbr lists match the current positions and order
+    bool rec_pos_valid = false;  // recA.lo / recB.lo mirror pv
+    bool rec_vel_valid = false;  // recA.hi mirrors vm
     int wmax = 1536;             // shared-memory window budget (slots) of the sweep kernels
     // per-kernel event timing (sph_profile_enable / sph_profile_read)
     cudaStream_t own_stream = nullptr;

@@ -137,8 +137,12 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_gather(Consts c, Dev d, int with_
     const int nfluid = __syncthreads_count(pv.w > 0.0f);
     if (threadIdx.x == 0) d.chunk_desc[(size_t)blockIdx.x * 40 + 2] = nfluid;
     if (k >= c.N) return;
+    const float4 vm = d.vm[i];
     d.pv_alt[k] = pv;
-    d.vm_alt[k] = d.vm[i];
+    d.vm_alt[k] = vm;
+    Rec ra; ra.lo = pv; ra.hi = vm;
+    d.recA[k] = ra;          // neighbour records of the list-based sweeps (sph_sweeps.cu)
+    d.recB[k].lo = pv;
     d.x0_alt[3 * k + 0] = d.x0[3 * i + 0];
     d.x0_alt[3 * k + 1] = d.x0[3 * i + 1];
     d.x0_alt[3 * k + 2] = d.x0[3 * i + 2];
@@ -257,5 +261,7 @@ int sph_sort_particles(SphHandle* h) {
     }
     h->sorted_valid = true;
     h->list_valid = false;
+    h->rec_pos_valid = c.N > 0;
+    h->rec_vel_valid = c.N > 0;
     return cudaGetLastError() == cudaSuccess ? SPH_OK : SPH_E_CUDA;
 }

@@ -1,19 +1,21 @@
-// sph_window.cuh — shared-memory neighbour windows staged by TMA bulk copies.
+// sph_window.cuh — shared-memory candidate windows staged by TMA bulk copies (neighbour-list build).
 //
 // A CTA owns a chunk of SPH_BLOCK consecutive particles of the cell-sorted SoA.  Because the
 // flatten is x-fastest, the 27-cell windows of all particles of the chunk are covered by at most 9
-// contiguous index ranges of the sorted arrays (one per (dz, dy) row offset, overlapping ranges
-// merged).  One elected thread issues cp.async.bulk (TMA, SASS UBLKCP) copies of those ranges of
-// every payload array the task reads (all payloads are float4 per particle, so any range is
-// 16-byte aligned) and the CTA waits on one mbarrier.  Afterwards every neighbour access is an
-// LDS.128 at a 16-bit window index: the neighbour lists store those indices (2 B per pair), and the
-// gathers that limited the global-memory version (one L1 wavefront per distinct 128-byte line per
-// load) become shared-memory reads.
+// contiguous index ranges of the sorted pv array (one per (dz, dy) row offset, overlapping ranges
+// merged).  One elected thread issues cp.async.bulk (TMA, SASS UBLKCP) copies of those ranges
+// (float4 per particle, so any range is 16-byte aligned) and the CTA waits on one mbarrier.  The
+// ~250 distance tests per particle of the build pass then read shared memory (threads of one cell
+// test the same candidate: broadcast, conflict-free) instead of issuing L1 requests.
+//
+// Measured (profiles/r01_*): staging windows for the list CONSUMERS (payload + 16-bit slot lists)
+// was 2x slower than gathering 32-byte records through L1 (low occupancy from 48 KB windows, long
+// scoreboard stalls on the list reads), so only the build pass uses the window.
 //
 // Descriptor per chunk (written once per sort by k_chunk_windows, 40 ints):
-//   [0] total window entries   [1] number of merged copies   [2..3] reserved
+//   [0] total window entries   [1] number of merged copies   [2] fluid rows in the chunk   [3] -
 //   [4..12]  gstart[r]  first sorted index of row-offset r's range
-//   [13..21] sbase[r]   window index of that first particle
+//   [13..21] sbase[r]   window slot of that first particle
 //   [22..30] cp_g[c]    merged copy c: first sorted index
 //   [31..39] cp_n[c]    merged copy c: particle count
 #pragma once
@@ -49,43 +51,14 @@ __device__ __forceinline__ void tma_bulk_load(void* smem_dst, const void* gsrc, 
                  : "memory");
 }
 
-// payload views: the same task body reads neighbour data either from the staged window (index =
-// window slot) or straight from global memory (index = sorted particle index; unstaged chunks)
-template <int NPAY>
-struct SmemView {
-    const float4* a[NPAY];
-    __device__ __forceinline__ float4 get(int which, int idx) const { return a[which][idx]; }
-};
-template <int NPAY>
-struct GlobalView {
-    const float4* a[NPAY];
-    __device__ __forceinline__ float4 get(int which, int idx) const { return __ldg(a[which] + idx); }
-};
-
-template <int NPAY>
 struct Window {
-    SmemView<NPAY> sv;
-    GlobalView<NPAY> gv;
+    const float4* s_pv;  // staged positions (+-V in w)
     const int* desc;     // shared copy of the chunk descriptor
     bool staged;
-    // sorted particle index of a window slot (rare paths: rigid wrench, debug)
-    __device__ __forceinline__ int global_index(int w) const {
-        const int ncp = desc[1];
-        int s = 0;
-        for (int c = 0; c < ncp; c++) {
-            const int n = desc[31 + c];
-            if (w < s + n) return desc[22 + c] + (w - s);
-            s += n;
-        }
-        return -1;
-    }
 };
 
-// Stage the chunk's window: call from all threads of the CTA, before any divergence.
-// payload[k] are the global float4 arrays; smem must hold wmax * NPAY float4.
-template <int NPAY>
-__device__ __forceinline__ Window<NPAY> window_open(const Dev& d, const float4* const (&payload)[NPAY], float4* smem, int wmax,
-                                                    int* s_desc, unsigned long long* s_mbar) {
+// Stage the chunk's pv window: call from all threads of the CTA, before any divergence.
+__device__ __forceinline__ Window window_open(const Dev& d, float4* smem, int wmax, int* s_desc, unsigned long long* s_mbar) {
     const int tid = threadIdx.x;
     if (tid < SPH_DESC_INTS) s_desc[tid] = d.chunk_desc[(size_t)blockIdx.x * SPH_DESC_INTS + tid];
     if (tid == 0) {
@@ -93,27 +66,21 @@ __device__ __forceinline__ Window<NPAY> window_open(const Dev& d, const float4* 
         fence_mbar_init();
     }
     __syncthreads();
-    Window<NPAY> w;
+    Window w;
     w.desc = s_desc;
+    w.s_pv = smem;
     const int total = s_desc[0];
     // chunks without fluid rows (as of the last sort) have nothing to sum: do not stage; a row that
     // turned fluid since (emitter) walks global memory instead
     w.staged = s_desc[2] > 0 && total <= wmax;
-#pragma unroll
-    for (int k = 0; k < NPAY; k++) {
-        w.sv.a[k] = smem + (size_t)k * wmax;
-        w.gv.a[k] = payload[k];
-    }
     if (w.staged) {
         if (tid == 0) {
-            mbar_arrive_expect_tx(s_mbar, (unsigned)total * 16u * NPAY);
+            mbar_arrive_expect_tx(s_mbar, (unsigned)total * 16u);
             const int ncp = s_desc[1];
             int s = 0;
             for (int c = 0; c < ncp; c++) {
                 const int g = s_desc[22 + c], n = s_desc[31 + c];
-#pragma unroll
-                for (int k = 0; k < NPAY; k++)
-                    tma_bulk_load(smem + (size_t)k * wmax + s, payload[k] + g, (unsigned)n * 16u, s_mbar);
+                tma_bulk_load(smem + s, d.pv + g, (unsigned)n * 16u, s_mbar);
                 s += n;
             }
         }
@@ -123,12 +90,12 @@ __device__ __forceinline__ Window<NPAY> window_open(const Dev& d, const float4* 
 }
 
 // Walk the 27-cell window of particle i with candidates read from the staged window.
-// visit(view, idx, pj, R, r2): idx is a window slot (view = smem) — accepted neighbours only.
-template <int NPAY, class Visit>
-__device__ __forceinline__ void window_walk(const Consts& c, const Dev& d, const Window<NPAY>& win, int i, float4 pi, Visit&& visit) {
+// visit(j, pj, R, r2) for every accepted neighbour j (sorted index), same order as for_all_neighbors.
+template <class Visit>
+__device__ __forceinline__ void window_walk(const Consts& c, const Dev& d, const Window& win, int i, float4 pi, Visit&& visit) {
     const int3 g = cell_of(c, pi.x, pi.y, pi.z);
     const int xlo = max(g.x - 1, 0), xhi = min(g.x + 1, c.nx - 1);
-    const float4* __restrict__ s_pv = win.sv.a[0];
+    const float4* __restrict__ s_pv = win.s_pv;
 #pragma unroll 1
     for (int dz = -1; dz <= 1; dz++) {
         const int zz = g.z + dz;
@@ -147,57 +114,8 @@ __device__ __forceinline__ void window_walk(const Consts& c, const Dev& d, const
                 const float4 pj = s_pv[w];
                 const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
                 const float r2 = dist2(R);
-                if (r2 < c.h2_thresh && j != i) visit(win.sv, w, pj, R, r2);
+                if (r2 < c.h2_thresh && j != i) visit(j, pj, R, r2);
             }
         }
     }
-}
-
-// Stream the 16-bit neighbour list of particle i; positions come from the staged window.
-template <int NPAY, class Visit>
-__device__ __forceinline__ void window_list(const Dev& d, const Window<NPAY>& win, int i, int n, float4 pi, Visit&& visit) {
-    const unsigned short* __restrict__ col = d.nbr16 + i;
-    const size_t stride = (size_t)d.nbr_stride;
-    const float4* __restrict__ s_pv = win.sv.a[0];
-    int k = 0;
-    for (; k + 4 <= n; k += 4) {
-        const int w0 = __ldg(col + (size_t)k * stride), w1 = __ldg(col + (size_t)(k + 1) * stride);
-        const int w2 = __ldg(col + (size_t)(k + 2) * stride), w3 = __ldg(col + (size_t)(k + 3) * stride);
-        const float4 p0 = s_pv[w0], p1 = s_pv[w1], p2 = s_pv[w2], p3 = s_pv[w3];
-        float3 R;
-        R = make_float3(pi.x - p0.x, pi.y - p0.y, pi.z - p0.z); visit(win.sv, w0, p0, R, dist2(R));
-        R = make_float3(pi.x - p1.x, pi.y - p1.y, pi.z - p1.z); visit(win.sv, w1, p1, R, dist2(R));
-        R = make_float3(pi.x - p2.x, pi.y - p2.y, pi.z - p2.z); visit(win.sv, w2, p2, R, dist2(R));
-        R = make_float3(pi.x - p3.x, pi.y - p3.y, pi.z - p3.z); visit(win.sv, w3, p3, R, dist2(R));
-    }
-    for (; k < n; k++) {
-        const int w = __ldg(col + (size_t)k * stride);
-        const float4 pj = s_pv[w];
-        const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        visit(win.sv, w, pj, R, dist2(R));
-    }
-}
-
-// Unstaged chunk (window larger than the shared-memory budget): walk the cells in global memory.
-template <int NPAY, class Visit>
-__device__ __forceinline__ void window_walk_global(const Consts& c, const Dev& d, const Window<NPAY>& win, int i, float4 pi, Visit&& visit) {
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) { visit(win.gv, j, pj, R, r2); });
-}
-
-// All neighbours of fluid particle i in walk order.  LIST: use the list recorded by the density
-// pass when the row fits (count <= kmax) and the chunk is staged; otherwise re-derive them.
-template <bool LIST, int NPAY, class Visit>
-__device__ __forceinline__ void window_neighbors(const Consts& c, const Dev& d, const Window<NPAY>& win, int i, float4 pi, Visit&& visit) {
-    if (!win.staged) {
-        window_walk_global(c, d, win, i, pi, visit);
-        return;
-    }
-    if (LIST) {
-        const int n = d.nbr_count[i];
-        if (n <= d.nbr_kmax) {
-            window_list(d, win, i, n, pi, visit);
-            return;
-        }
-    }
-    window_walk(c, d, win, i, pi, visit);
 }
