@@ -80,7 +80,7 @@ def dam_break_scene(method="dfsph", scale=1.0, n_slabs=1):
     return {"Configuration": cfg, "FluidBlocks": [block]}
 
 
-def make_sim(scene_dict, lib=None, device=0):
+def make_sim(scene_dict, lib=None, device=0, slab=None):
     from sph_project_b200.containers import DFSPHContainer, WCSPHContainer
     from sph_project_b200.fluid_solvers import DFSPHSolver, WCSPHSolver
     from sph_project_b200.utils import SimConfig
@@ -88,7 +88,7 @@ def make_sim(scene_dict, lib=None, device=0):
     C, S = (DFSPHContainer, DFSPHSolver) if cfg.get_cfg("simulationMethod") == "dfsph" else (WCSPHContainer, WCSPHSolver)
     import contextlib
     with contextlib.redirect_stdout(sys.stderr):
-        container = C(cfg, GGUI=False, engine_library=lib, device=device)
+        container = C(cfg, GGUI=False, engine_library=lib, device=device, slab=slab)
         solver = S(container)
         solver.prepare()
     return container, solver
@@ -229,7 +229,6 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        raise SystemExit("multi-GPU Z-slab path: see bench_slab (not built in this revision)")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -238,9 +237,12 @@ def run_gpu(args, rank, world, local_rank):
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
 
     t_setup = time.perf_counter()
-    container, solver = make_sim(dam_break_scene("dfsph"), device=local_rank)
+    # N > 1: weak scaling, the domain and the block grow along z by one 1.23M-particle slab per GPU
+    container, solver = make_sim(dam_break_scene("dfsph", n_slabs=world), device=local_rank,
+                                 slab=(rank, world) if world > 1 else None)
     eng = container.engine
-    n_fluid, n_total = int(container.fluid_particle_num[None]), int(container.particle_num[None])
+    n_fluid, n_total = int(container.fluid_particle_num[None]), int(container.global_particle_num)
+    n_local = int(container.particle_num[None])
     stream = torch.cuda.Stream()
     eng.set_stream(stream.cuda_stream)
 
@@ -301,15 +303,17 @@ def run_gpu(args, rank, world, local_rank):
     total_kernel_ms = sum(v[1] for v in prof.values())
     top = sorted(prof.items(), key=lambda kv: -kv[1][1])
     from sph_project_b200._native import F as _F
-    mat_now = container.particle_materials.to_numpy(n_total)
-    n_pairs = int(eng.get_field(_F.NEIGHBOR_COUNT, n_total)[mat_now == 1].sum())
+    n_local = int(container.particle_num[None])
+    mat_now = container.particle_materials.to_numpy(n_local)
+    n_pairs = int(eng.get_field(_F.NEIGHBOR_COUNT, n_local)[(mat_now == 1) & container.owned_mask()].sum())
+    n_rows = n_local   # kernels of this rank stream this rank's particles
     kernels = []
     for k, v in top[:10]:
-        ab = algo_bytes(k, n_total, n_pairs)
+        ab = algo_bytes(k, n_rows, n_pairs)
         kernels.append({"name": k, "launches": int(v[0]), "ms_per_launch": v[1] / v[0], "share": v[1] / total_kernel_ms,
                         "algo_GBps": (ab / (v[1] / v[0] * 1e-3) / 1e9) if ab else None})
     dom_name, (dom_launches, dom_ms) = top[0]
-    dom_bytes = algo_bytes(dom_name, n_total, n_pairs) or 0
+    dom_bytes = algo_bytes(dom_name, n_rows, n_pairs) or 0
     achieved = dom_bytes / (dom_ms / dom_launches * 1e-3) / 1e9
     roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
@@ -320,8 +324,9 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- e2e: host buffers in and out every step, through the C ABI ----
     from sph_project_b200._native import F
-    xh = torch.empty((n_total, 3), dtype=torch.float32, pin_memory=True).numpy()
-    vh = torch.empty((n_total, 3), dtype=torch.float32, pin_memory=True).numpy()
+    n_local = int(container.particle_num[None])
+    xh = torch.empty((n_local, 3), dtype=torch.float32, pin_memory=True).numpy()
+    vh = torch.empty((n_local, 3), dtype=torch.float32, pin_memory=True).numpy()
     eng.get_field_into(F.POSITION, xh)
     eng.get_field_into(F.VELOCITY, vh)
     e2e_steps = max(3, min(args.steps, 10))
@@ -336,8 +341,12 @@ def run_gpu(args, rank, world, local_rank):
         eng.get_field_into(F.VELOCITY, vh)
     barrier()
     e2e_s = time.perf_counter() - t0
-    e2e = {"value": n_fluid * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(xh.nbytes + vh.nbytes),
-           "d2h_bytes_per_step": int(xh.nbytes + vh.nbytes), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": n_fluid * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(xh.nbytes + vh.nbytes) * world,
+           "d2h_bytes_per_step": int(xh.nbytes + vh.nbytes) * world, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
            "what": "pinned host x,v -> sph_set_field x2 -> sph_step(1) -> sph_get_field x2 -> pinned host"}
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1) ----

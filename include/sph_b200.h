@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SPH_ABI_VERSION 4
+#define SPH_ABI_VERSION 5
 #define SPH_MAX_OBJECTS 20 /* base_container.py:52 max_num_object */
 
 /* error codes */
@@ -299,30 +299,31 @@ typedef struct SphKernelStat {
 int sph_profile_enable(SphHandle* h, int32_t enable);
 int sph_profile_read(SphHandle* h, SphKernelStat* out, int32_t capacity, int32_t* count);
 
-/* ---- Z-slab sharding (no reference counterpart) ----------------------- */
-/* A slab handle owns cells cz in [z_lo, z_hi) and keeps imported ghost particles of the
- * layers z_lo-1 and z_hi.  The host (torch.distributed / NCCL) moves the packed buffers. */
+/* ---- Z-slab sharding across the GPUs of one box (no reference counterpart) ----
+ * One process + one handle (created with SPH_FLAG_SLAB) per GPU.  A slab owns the cell layers cz in
+ * [z_lo, z_hi) of the GLOBAL grid and mirrors its neighbours' boundary layers z_lo-1 and z_hi as
+ * read-only ghosts.  Migration, ghost import, per-field halo refreshes and the solver loops' error
+ * sums run inside the library over NCCL (ncclSend/ncclRecv/ncclAllReduce on the handle's stream);
+ * the host only brokers the NCCL unique id (e.g. with torch.distributed.broadcast).
+ * Supported solvers: WCSPH and DFSPH with standard viscosity. */
+#define SPH_SLAB_RECORD_WORDS 24   /* 32-bit words per migrating / ghost particle record */
 typedef struct SphSlabInfo {
-    int32_t z_lo, z_hi;        /* owned cell layers */
-    int32_t n_owned;           /* particles with cz in [z_lo, z_hi) */
-    int32_t n_ghost;           /* imported ghosts */
-    int32_t n_send_lo, n_send_hi; /* boundary-layer particles exported to rank-1 / rank+1 */
+    int32_t z_lo, z_hi;           /* owned cell layers */
+    int32_t n_owned;              /* particles with cz in [z_lo, z_hi) after the last sort */
+    int32_t n_ghost;              /* imported ghosts */
+    int32_t n_send_lo, n_send_hi; /* my boundary layers = the neighbours' ghost layers */
+    int32_t own_begin, own_end;   /* owned index range of the sorted arrays */
+    int64_t halo_bytes;           /* bytes sent so far (migration + ghosts + halo refreshes) */
+    int64_t halo_calls;           /* halo refreshes so far */
 } SphSlabInfo;
-int sph_slab_set_range(SphHandle* h, int32_t z_lo, int32_t z_hi);
+/* rank 0 creates the id (ncclGetUniqueId); every rank passes the same 128 bytes to sph_slab_init */
+int sph_slab_unique_id(void* out128);
+/* collective over all ranks: creates the communicator; add particles (owned ones only) afterwards.
+ * global_particle_num = particle_num of the whole domain (DFSPH error normalisation, DFSPH.py:211,294) */
+int sph_slab_init(SphHandle* h, int32_t rank, int32_t world, const void* unique_id128, int32_t z_lo, int32_t z_hi,
+                  int64_t global_particle_num);
+int sph_slab_set_global_particle_num(SphHandle* h, int64_t n);
 int sph_slab_info(SphHandle* h, SphSlabInfo* out);
-/* Drop ghosts; split owned particles into stay / leave-low / leave-high (migration) and
- * count the boundary-layer exports.  Packed record = SPH_SLAB_RECORD_FLOATS 32-bit words. */
-#define SPH_SLAB_RECORD_WORDS 24
-int sph_slab_begin_exchange(SphHandle* h, int32_t counts[4] /* mig_lo, mig_hi, ghost_lo, ghost_hi */);
-/* device pointers of the packed send buffers (side 0 = low neighbour, 1 = high) */
-int sph_slab_pack(SphHandle* h, int32_t kind /*0 migrate, 1 ghost*/, int32_t side, void** dev_ptr, int32_t* n_records);
-/* append n received records (device pointer) as owned (kind 0) or ghost (kind 1) particles */
-int sph_slab_unpack(SphHandle* h, int32_t kind, int32_t side, const void* dev_ptr, int32_t n_records);
-/* After the sort: per-field halo refresh. pack gathers the field of my boundary-layer
- * particles for `side`; unpack scatters a received buffer into my ghosts of `side`. */
-int sph_slab_halo_pack(SphHandle* h, int32_t field, int32_t side, void** dev_ptr, int32_t* n, int32_t* words_per_item);
-int sph_slab_halo_unpack(SphHandle* h, int32_t field, int32_t side, const void* dev_ptr, int32_t n);
-int sph_slab_halo_recv_count(SphHandle* h, int32_t side, int32_t* n);
 
 #ifdef __cplusplus
 }

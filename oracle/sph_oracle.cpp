@@ -1284,13 +1284,9 @@ int sph_profile_enable(SphHandle*, int32_t) { return SPH_OK; }
 int sph_profile_read(SphHandle*, SphKernelStat*, int32_t, int32_t* count) { if (count) *count = 0; return SPH_OK; }
 
 // Z-slab sharding is a property of the CUDA product; the oracle always holds the whole domain.
-int sph_slab_set_range(SphHandle* h, int32_t, int32_t) { return fail(h, SPH_E_UNSUPPORTED, "oracle holds the whole domain"); }
+int sph_slab_unique_id(void*) { return SPH_E_UNSUPPORTED; }
+int sph_slab_init(SphHandle* h, int32_t, int32_t, const void*, int32_t, int32_t, int64_t) { return fail(h, SPH_E_UNSUPPORTED, "oracle holds the whole domain"); }
+int sph_slab_set_global_particle_num(SphHandle* h, int64_t) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
 int sph_slab_info(SphHandle* h, SphSlabInfo*) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
-int sph_slab_begin_exchange(SphHandle* h, int32_t*) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
-int sph_slab_pack(SphHandle* h, int32_t, int32_t, void**, int32_t*) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
-int sph_slab_unpack(SphHandle* h, int32_t, int32_t, const void*, int32_t) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
-int sph_slab_halo_pack(SphHandle* h, int32_t, int32_t, void**, int32_t*, int32_t*) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
-int sph_slab_halo_unpack(SphHandle* h, int32_t, int32_t, const void*, int32_t) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
-int sph_slab_halo_recv_count(SphHandle* h, int32_t, int32_t*) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
 
 }  // extern "C"

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_OBJECTS = 20
 
 METHOD_WCSPH, METHOD_PCISPH, METHOD_DFSPH = 0, 1, 2
@@ -54,7 +54,8 @@ class SphKernelStat(C.Structure):
 
 class SphSlabInfo(C.Structure):
     _fields_ = [("z_lo", C.c_int32), ("z_hi", C.c_int32), ("n_owned", C.c_int32), ("n_ghost", C.c_int32),
-                ("n_send_lo", C.c_int32), ("n_send_hi", C.c_int32)]
+                ("n_send_lo", C.c_int32), ("n_send_hi", C.c_int32), ("own_begin", C.c_int32), ("own_end", C.c_int32),
+                ("halo_bytes", C.c_int64), ("halo_calls", C.c_int64)]
 
 
 class F:
@@ -175,14 +176,10 @@ PROTOTYPES = {
     "sph_set_stream": (C.c_int, [_H, C.c_void_p]),
     "sph_profile_enable": (C.c_int, [_H, C.c_int32]),
     "sph_profile_read": (C.c_int, [_H, C.POINTER(SphKernelStat), C.c_int32, _i32p]),
-    "sph_slab_set_range": (C.c_int, [_H, C.c_int32, C.c_int32]),
+    "sph_slab_unique_id": (C.c_int, [C.c_void_p]),
+    "sph_slab_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
+    "sph_slab_set_global_particle_num": (C.c_int, [_H, C.c_int64]),
     "sph_slab_info": (C.c_int, [_H, C.POINTER(SphSlabInfo)]),
-    "sph_slab_begin_exchange": (C.c_int, [_H, _i32p]),
-    "sph_slab_pack": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _i32p]),
-    "sph_slab_unpack": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
-    "sph_slab_halo_pack": (C.c_int, [_H, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _i32p, _i32p]),
-    "sph_slab_halo_unpack": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
-    "sph_slab_halo_recv_count": (C.c_int, [_H, C.c_int32, _i32p]),
 }
 
 
@@ -392,8 +389,20 @@ class Engine:
         return {rows[i].name.decode(): (rows[i].launches, rows[i].total_ms) for i in range(count.value)}
 
     # -- slabs --
-    def slab_set_range(self, z_lo: int, z_hi: int):
-        self._check(self.lib.sph_slab_set_range(self._h, int(z_lo), int(z_hi)))
+    def slab_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.sph_slab_unique_id(buf)
+        if rc != 0:
+            raise SphError(rc, "sph_slab_unique_id (is NCCL loaded in this process?)")
+        return buf.raw
+
+    def slab_init(self, rank: int, world: int, unique_id: bytes, z_lo: int, z_hi: int, global_particle_num: int):
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(unique_id, 128)
+        self._check(self.lib.sph_slab_init(self._h, int(rank), int(world), buf, int(z_lo), int(z_hi), int(global_particle_num)))
+
+    def slab_set_global_particle_num(self, n: int):
+        self._check(self.lib.sph_slab_set_global_particle_num(self._h, int(n)))
 
     def slab_info(self) -> SphSlabInfo:
         info = SphSlabInfo()

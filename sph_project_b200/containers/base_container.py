@@ -125,9 +125,23 @@ class BaseContainer:
         self.particle_max_num = int(fluid_particle_num + rigid_body_particle_num + box_particles)
         print(f"Fluid particle num: {fluid_particle_num}, Rigid body particle num: {rigid_body_particle_num}")
 
+        # ---- Z-slab sharding (multi-GPU; not upstream): this rank keeps the particles of its slab ----
+        self.global_particle_num = self.particle_max_num
+        self.slab = None
+        self._next_uid = 0
+        if slab:
+            self.slab = self._make_slab_context(*slab)
+            self.particle_max_num = self.slab.capacity(self._layer_counts)
+
         # ---- device state: one library handle instead of ~35 Taichi fields (:129-190) ----
-        self._engine = nat.Engine(self._make_params(device, slab), lib=engine_library)
+        self._engine = nat.Engine(self._make_params(device, bool(slab)), lib=engine_library)
         eng, cap = self._engine, self.particle_max_num
+        if self.slab is not None:
+            from ..slab import broadcast_bytes
+            uid = self._engine.slab_unique_id() if self.slab.rank == 0 else None
+            uid = broadcast_bytes(uid, 128, src=0)
+            self._engine.slab_init(self.slab.rank, self.slab.world, uid, self.slab.z_lo, self.slab.z_hi,
+                                   self.global_particle_num)
 
         self.particle_num = ScalarField(eng, S.PARTICLE_NUM, int)
         self.fluid_particle_num = ScalarField(eng, S.FLUID_PARTICLE_NUM, int)
@@ -214,6 +228,43 @@ class BaseContainer:
     def engine(self) -> nat.Engine:
         return self._engine
 
+    def _scene_positions(self):
+        """Every particle the scene will ever insert (box, blocks, mesh bodies), for the slab split."""
+        parts = []
+        if self.add_domain_box:
+            parts.append(self._box_shell(self.domain_box_start, self.domain_box_size, self.domain_box_thickness,
+                                         self.particle_spacing))
+        for fluid in self.fluid_blocks:
+            offset = np.array(fluid["translation"])
+            start = np.array(fluid["start"]) + offset
+            end = np.array(fluid["end"]) + offset
+            parts.append(_lattice(start, (end - start) * np.array(fluid["scale"]), self.particle_spacing, self.dim))
+        for body in list(self.fluid_bodies) + list(self.rigid_bodies):
+            parts.append(np.asarray(body["voxelizedPoints"], dtype=np.float32))
+        return parts
+
+    def _make_slab_context(self, rank, world):
+        from ..slab import SlabContext, balanced_ranges, cell_layer
+        nz = int(self.grid_num[2])
+        counts = np.zeros(nz, dtype=np.int64)
+        for pos in self._scene_positions():
+            if len(pos):
+                counts += np.bincount(cell_layer(pos[:, 2], self.dh, nz), minlength=nz)
+        self._layer_counts = counts
+        return SlabContext(rank=int(rank), world=int(world), dh=float(self.dh), nz=nz,
+                           ranges=balanced_ranges(counts, int(world)))
+
+    def owned_mask(self):
+        """Live particles this rank owns (everything unless the container is a Z-slab: then not the ghosts)."""
+        n = self.particle_num[None]
+        mask = np.ones(n, dtype=bool)
+        if self.slab is not None:
+            info = self._engine.slab_info()
+            if info.own_end > info.own_begin or info.n_ghost:
+                mask[:] = False
+                mask[info.own_begin:info.own_end] = True
+        return mask
+
     def _push_object(self, obj_id):
         self._engine.set_object(obj_id, int(self.object_materials[obj_id]), int(self.rigid_body_is_dynamic[obj_id]))
 
@@ -297,10 +348,28 @@ class BaseContainer:
                       new_particle_density, new_particle_pressure, new_particles_material,
                       new_particles_is_dynamic, new_particles_color):
         """Append particles (base_container.py:417-464); host arrays are copied to the device."""
-        assert new_particles_num == np.asarray(new_particles_positions).reshape(-1, self.dim).shape[0]
-        self._engine.add_particles(object_id, new_particles_positions, new_particles_velocity, new_particle_density,
-                                   new_particle_pressure, new_particles_material, new_particles_is_dynamic,
-                                   new_particles_color)
+        positions = np.asarray(new_particles_positions, dtype=np.float32).reshape(-1, self.dim)
+        assert new_particles_num == positions.shape[0]
+        if self.slab is None:
+            self._engine.add_particles(object_id, positions, new_particles_velocity, new_particle_density,
+                                       new_particle_pressure, new_particles_material, new_particles_is_dynamic,
+                                       new_particles_color)
+            self._next_uid += new_particles_num
+            return
+        # Z-slab: keep my layers only; uids stay the global insertion indices
+        keep = self.slab.owned(positions)
+        uids = (self._next_uid + np.arange(new_particles_num, dtype=np.int32))[keep]
+        self._next_uid += new_particles_num
+        if not keep.any():
+            return
+        pick = lambda a, w: np.asarray(a).reshape(new_particles_num, *([w] if w > 1 else []))[keep]
+        n_before = self.particle_num[None]
+        self._engine.add_particles(object_id, positions[keep], pick(new_particles_velocity, self.dim),
+                                   pick(new_particle_density, 1), pick(new_particle_pressure, 1),
+                                   pick(new_particles_material, 1), pick(new_particles_is_dynamic, 1),
+                                   pick(new_particles_color, 3))
+        all_uids = np.concatenate([self._engine.get_field(F.UID, n_before), uids])
+        self._engine.set_field(F.UID, all_uids)
 
     def _add_lattice(self, object_id, positions, material, is_dynamic, color, density, pressure, velocity):
         n = positions.shape[0]

@@ -28,7 +28,27 @@ int check_cuda(SphHandle* h, cudaError_t e, const char* what) {
         if (_rc) return _rc;                              \
     } while (0)
 
-int last_launch(SphHandle* h) { return check_cuda(h, cudaGetLastError(), "kernel launch"); }
+int last_launch(SphHandle* h) {
+    if (h->sticky_rc) {   // an NCCL halo inside a launcher failed; message is already in h->err
+        const int rc = h->sticky_rc;
+        h->sticky_rc = 0;
+        return rc;
+    }
+    return check_cuda(h, cudaGetLastError(), "kernel launch");
+}
+
+// rows the kernels update: everything, unless the handle is a Z-slab (then set by the sort)
+void rows_all(SphHandle* h) {
+    if (!h->slab) {
+        h->c.row_begin = 0;
+        h->c.row_end = h->c.N;
+    } else if (!h->sorted_valid) {
+        h->c.row_begin = 0;          // before the first exchange every local particle is owned
+        h->c.row_end = h->c.N;
+    }
+}
+// particle_num of the whole domain (DFSPH error normalisation, DFSPH.py:211,294)
+float global_particle_num(const SphHandle* h) { return h->slab ? (float)h->n_global : (float)h->c.N; }
 
 template <class T>
 int dev_alloc(SphHandle* h, T*& p, size_t count) {
@@ -139,8 +159,9 @@ int dfsph_correct_divergence_error(SphHandle* h, int* iters, float* err) {
         sph_launch_dfsph_correct_divergence(h, true);
         if ((rc = zero_red(h, RED_ERR))) return rc;
         sph_launch_dfsph_density_derivative(h, true);
+        if ((rc = sph_slab_allreduce_red(h, RED_ERR, 1))) return rc;
         if ((rc = read_red(h))) return rc;   // the reference's per-iteration device->host read
-        e = (float)h->h_red[RED_ERR] / (float)c.N;
+        e = (float)h->h_red[RED_ERR] / global_particle_num(h);
         const float eta = 0.001f * c.rho0 / c.dt;
         it++;
         if (e <= eta) break;
@@ -159,8 +180,9 @@ int dfsph_correct_density_error(SphHandle* h, int* iters, float* err) {
         sph_launch_dfsph_correct_density(h, true);
         if ((rc = zero_red(h, RED_ERR))) return rc;
         sph_launch_dfsph_density_star(h, true);
+        if ((rc = sph_slab_allreduce_red(h, RED_ERR, 1))) return rc;
         if ((rc = read_red(h))) return rc;
-        e = (float)h->h_red[RED_ERR] / (float)c.N;
+        e = (float)h->h_red[RED_ERR] / global_particle_num(h);
         it++;
         if (e <= 0.0001f) break;
     }
@@ -386,7 +408,7 @@ int sph_create(const SphParams* p, SphHandle** out) {
         ALLOC(d.cg_p, n); ALLOC(d.v_orig, n); ALLOC(d.cg_Ap, n); ALLOC(d.cg_x, n); ALLOC(d.cg_b, n); ALLOC(d.cg_r, n);
         ALLOC(d.cg_dinv, 9 * n);
     }
-    ALLOC(d.cell_count, (size_t)c.ncell); ALLOC(d.cell_start, (size_t)c.ncell + 1);
+    ALLOC(d.cell_count, (size_t)c.ncell + 8); ALLOC(d.cell_start, (size_t)c.ncell + 8);   // + the slab trash cell
     ALLOC(d.rank, n); ALLOC(d.perm, n);
     {
         const size_t m = (size_t)(c.ncell > c.cap ? c.ncell : c.cap);
@@ -434,6 +456,7 @@ int sph_destroy(SphHandle* h) {
     if (!h) return SPH_OK;
     cudaSetDevice(h->P.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    sph_slab_free(h);
     for (void* p : h->allocations) cudaFree(p);
     if (h->h_red) cudaFreeHost(h->h_red);
     for (auto& r : h->prof) { cudaEventDestroy(r.begin); cudaEventDestroy(r.end); }
@@ -687,6 +710,7 @@ int sph_compute_rigid_body_mass(SphHandle* h, int32_t object_id, float* out) {
 
 int sph_prepare_neighborhood_search(SphHandle* h) {
     if (!h) return SPH_E_INVALID;
+    rows_all(h);
     int rc = update_dynamic_rigid_flag(h);
     if (rc) return rc;
     rc = sph_sort_particles(h);
@@ -746,6 +770,9 @@ int sph_get_grid_num_particles(SphHandle* h, int32_t* dst, size_t count) {
 
 int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
     if (!h) return SPH_E_INVALID;
+    rows_all(h);
+    if (h->slab && ((task >= SPH_T_CG_PREPARE1 && task <= SPH_T_COPY_BACK_ORIGINAL_VELOCITY) || task >= SPH_T_PCISPH_COMPUTE_PREDICTED_VELOCITY))
+        return fail(h, SPH_E_UNSUPPORTED, "Z-slab handles support WCSPH and DFSPH with standard viscosity");
     int rc = update_dynamic_rigid_flag(h);
     if (rc) return rc;
     const bool implicit = h->P.visc_method == SPH_VISC_IMPLICIT;
@@ -799,8 +826,9 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
             if ((rc = zero_red(h, RED_ERR))) return rc;
             if (task == SPH_T_DFSPH_COMPUTE_DENSITY_ERROR) sph_launch_dfsph_density_error(h);
             else sph_launch_dfsph_divergence_error(h);
+            if ((rc = sph_slab_allreduce_red(h, RED_ERR, 1))) return rc;
             if ((rc = read_red(h))) return rc;
-            if (out) *out = (float)h->h_red[RED_ERR] / (float)h->c.N;
+            if (out) *out = (float)h->h_red[RED_ERR] / global_particle_num(h);
             break;
         case SPH_T_DFSPH_COMPUTE_KAPPA: sph_launch_dfsph_kappa(h); break;
         case SPH_T_DFSPH_CORRECT_DENSITY_ERROR_STEP: sph_launch_dfsph_correct_density(h, false); break;
@@ -822,6 +850,9 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
 
 int sph_step(SphHandle* h, int32_t n_steps, SphStepStats* stats) {
     if (!h || n_steps < 0) return SPH_E_INVALID;
+    rows_all(h);
+    if (h->slab && (h->P.method == SPH_METHOD_PCISPH || h->P.visc_method == SPH_VISC_IMPLICIT))
+        return fail(h, SPH_E_UNSUPPORTED, "Z-slab handles support WCSPH and DFSPH with standard viscosity");
     int rc = update_dynamic_rigid_flag(h);
     if (rc) return rc;
     SphStepStats st;
@@ -839,6 +870,7 @@ int sph_step(SphHandle* h, int32_t n_steps, SphStepStats* stats) {
 
 int sph_dfsph_correct_density_error(SphHandle* h, int32_t* it, float* e) {
     if (!h) return SPH_E_INVALID;
+    rows_all(h);
     int i; float err;
     int rc = dfsph_correct_density_error(h, &i, &err);
     if (it) *it = i;
@@ -847,6 +879,7 @@ int sph_dfsph_correct_density_error(SphHandle* h, int32_t* it, float* e) {
 }
 int sph_dfsph_correct_divergence_error(SphHandle* h, int32_t* it, float* e) {
     if (!h) return SPH_E_INVALID;
+    rows_all(h);
     int i; float err;
     int rc = dfsph_correct_divergence_error(h, &i, &err);
     if (it) *it = i;
@@ -855,6 +888,7 @@ int sph_dfsph_correct_divergence_error(SphHandle* h, int32_t* it, float* e) {
 }
 int sph_pcisph_refine(SphHandle* h, int32_t* it, float* e) {
     if (!h) return SPH_E_INVALID;
+    rows_all(h);
     int i; float err;
     int rc = pcisph_refine(h, &i, &err);
     if (it) *it = i;
@@ -863,6 +897,7 @@ int sph_pcisph_refine(SphHandle* h, int32_t* it, float* e) {
 }
 int sph_implicit_viscosity_solve(SphHandle* h, int32_t* it, float* e) {
     if (!h) return SPH_E_INVALID;
+    rows_all(h);
     if (h->P.visc_method != SPH_VISC_IMPLICIT) return fail(h, SPH_E_STATE, "viscosityMethod is not implicit");
     int i; float err;
     int rc = implicit_viscosity_solve(h, &i, &err);

@@ -39,7 +39,12 @@ struct Consts {
     float dom_x, dom_y, dom_z, padding;
     float pcisph_k;
     int z_lo, z_hi;   // owned cell layers (whole grid unless the handle is a slab)
+    int row_begin, row_end;   // rows the kernels update: [0, N) or, for a Z-slab, the owned index range
 };
+
+// per-particle work happens for owned rows only; ghost rows (Z-slabs) are read-only neighbours
+#define SPH_ROW_OR_RETURN(c, i) if ((i) < (c).row_begin || (i) >= (c).row_end) return
+#define SPH_IS_ROW(c, i) ((i) >= (c).row_begin && (i) < (c).row_end)
 
 // 32-byte neighbour record: one 256-bit load (LDG.E.256, sm_100+) fetches everything a sweep needs
 // about neighbour j.  lo = pv (x, y, z, +-V); hi = the per-sweep payload.
@@ -208,6 +213,11 @@ struct SphHandle {
     bool list_valid = false;     // nbr lists match the current positions and order
     bool rec_pos_valid = false;  // recA.lo / recB.lo mirror pv
     bool rec_vel_valid = false;  // recA.hi mirrors vm
+    // Z-slab state (sph_slab.cu); ghost_stale = fields whose ghost copies lag their owners
+    struct SlabState* slab = nullptr;
+    long long n_global = 0;
+    int ghost_stale = 0;
+    int sticky_rc = 0;           // first error raised inside a void launcher (NCCL), reported by the caller
     int wmax = 1536;             // shared-memory window budget (slots) of the sweep kernels
     // per-kernel event timing (sph_profile_enable / sph_profile_read)
     cudaStream_t own_stream = nullptr;

@@ -17,11 +17,14 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-__global__ void __launch_bounds__(SPH_BLOCK) k_cell_index(Consts c, Dev d) {
+// slab: retired particles (ghosts of the previous step, particles that migrated away) are binned
+// into a trash cell behind the grid, so the sort itself drops them
+__global__ void __launch_bounds__(SPH_BLOCK) k_cell_index(Consts c, Dev d, int slab) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
     float4 p = d.pv[i];
     int flat = flatten(c, cell_of(c, p.x, p.y, p.z));
+    if (slab && d.ghost_slot[i] == 2) flat = c.ncell;
     d.grid_id[i] = flat;
     d.rank[i] = atomicAdd(d.cell_count + flat, 1);
 }
@@ -228,19 +231,32 @@ int sph_sort_particles(SphHandle* h) {
     Consts& c = h->c;
     Dev& d = h->d;
     cudaStream_t st = h->stream;
-    cudaMemsetAsync(d.cell_count, 0, sizeof(int) * (size_t)c.ncell, st);
-    const int nb = (c.N + SPH_BLOCK - 1) / SPH_BLOCK;
+    const bool slab = sph_is_slab(h);
+    int rc;
+    if (slab && (rc = sph_slab_pre_sort(h))) return rc;   // migration + ghost import (appends, retires)
+    cudaMemsetAsync(d.cell_count, 0, sizeof(int) * ((size_t)c.ncell + 1), st);
+    int nb = (c.N + SPH_BLOCK - 1) / SPH_BLOCK;
     if (c.N > 0) {
         SphProf p(h, "k_cell_index");
-        k_cell_index<<<nb, SPH_BLOCK, 0, st>>>(c, d);
+        k_cell_index<<<nb, SPH_BLOCK, 0, st>>>(c, d, slab ? 1 : 0);
         h->launches++;
     }
-    sph_exclusive_scan(h, d.cell_count, c.ncell, d.cell_start);
+    sph_exclusive_scan(h, d.cell_count, c.ncell + 1, d.cell_start);
     if (c.N > 0) {
         { SphProf p(h, "k_scatter_perm"); k_scatter_perm<<<nb, SPH_BLOCK, 0, st>>>(c, d); }
+        h->launches++;
+    }
+    if (slab) {
+        if ((rc = sph_slab_post_scan(h))) return rc;   // live count, owned range, halo ranges (one host sync)
+        nb = (c.N + SPH_BLOCK - 1) / SPH_BLOCK;
+    } else {
+        c.row_begin = 0;
+        c.row_end = c.N;
+    }
+    if (c.N > 0) {
         { SphProf p(h, "k_sort_cells"); k_sort_cells<<<(c.ncell + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, st>>>(c, d); }
-        { SphProf p(h, "k_gather"); k_gather<<<nb, SPH_BLOCK, 0, st>>>(c, d, (h->P.flags & SPH_FLAG_SLAB) ? 1 : 0); }
-        h->launches += 3;
+        { SphProf p(h, "k_gather"); k_gather<<<nb, SPH_BLOCK, 0, st>>>(c, d, slab ? 1 : 0); }
+        h->launches += 2;
         swap_ptr(d.pv, d.pv_alt);
         swap_ptr(d.vm, d.vm_alt);
         swap_ptr(d.x0, d.x0_alt);
@@ -263,5 +279,6 @@ int sph_sort_particles(SphHandle* h) {
     h->list_valid = false;
     h->rec_pos_valid = c.N > 0;
     h->rec_vel_valid = c.N > 0;
+    h->ghost_stale = 0;   // the ghosts were just re-imported with their owners' current state
     return cudaGetLastError() == cudaSuccess ? SPH_OK : SPH_E_CUDA;
 }

@@ -33,6 +33,18 @@ __device__ __forceinline__ void block_reduce_add(double* dst, double v) {
 }
 #endif
 
+// sph_slab.cu
+enum GhostField { GHOST_VEL = 1, GHOST_AUX = 2, GHOST_RHO = 4, GHOST_PV = 8 };
+bool sph_is_slab(const SphHandle* h);
+int sph_slab_pre_sort(SphHandle* h);
+int sph_slab_post_scan(SphHandle* h);
+int sph_slab_halo(SphHandle* h, void* base, int elem_bytes);
+int sph_slab_allreduce_red(SphHandle* h, int slot, int count);
+void sph_slab_free(SphHandle* h);
+// mark / refresh ghost copies (no-ops unless the handle is a slab)
+inline void sph_ghost_dirty(SphHandle* h, int what) { if (h->slab) h->ghost_stale |= what; }
+void sph_ghost_sync(SphHandle* h, int what);
+
 // sph_grid.cu
 void sph_exclusive_scan(SphHandle* h, const int* in, int n, int* out);
 int sph_sort_particles(SphHandle* h);

@@ -1,18 +1,379 @@
-// sph_slab.cu — Z-slab sharding entry points; filled in by the multi-GPU milestone.
+// sph_slab.cu — Z-slab domain decomposition across the GPUs of one NVSwitch box;
+// no counterpart in the reference, which is single-device.
+//
+// One process / handle per GPU.  Rank r owns the cell layers cz in [z_lo, z_hi) of the global grid
+// and keeps read-only copies ("ghosts") of the neighbouring ranks' boundary layers z_lo-1 and z_hi
+// (support radius = cell size, so one layer suffices for every sweep).  Because the flatten is
+// z-slowest and the sort is stable, after every sort
+//   [ghost layer z_lo-1][owned layers ...][ghost layer z_hi]
+// are three contiguous index ranges, and my boundary layer z_lo (z_hi-1) holds exactly the particles
+// of the lower (upper) neighbour's ghost layer, in the same order.  A halo refresh of any field is
+// therefore a plain contiguous ncclSend/ncclRecv of an index range — no pack kernels, no index maps.
+//
+// Once per step, before the sort, particles that left the slab migrate to the neighbour and the
+// ghost layers are re-imported (full particle records); inside the solver loops only the fields a
+// sweep's inputs changed are refreshed: recA (velocities) and recB (kappa) twice per DFSPH iteration,
+// plus one ncclAllReduce of the error sum.  All NCCL calls are enqueued on the handle's stream.
+//
+// NCCL is resolved at run time from the process (torch has already loaded libnccl.so.2); the
+// communicator is created from a unique id that the Python host broadcasts with torch.distributed.
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+
 #include "sph_kernels.h"
 
-static int unsupported(SphHandle* h) {
-    if (h) h->err = "Z-slab sharding is not built yet";
-    return SPH_E_UNSUPPORTED;
+// ---- minimal NCCL ABI (stable across NCCL 2.x) ---------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt8 = 0, ncclInt32 = 2, ncclFloat32 = 7, ncclFloat64 = 8 };
+enum { ncclSum = 0 };
+struct NcclApi {
+    int (*GetUniqueId)(ncclUniqueId*);
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+    int (*CommDestroy)(ncclComm_t);
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*GroupStart)();
+    int (*GroupEnd)();
+    const char* (*GetErrorString)(int);
+    bool ok = false;
+};
+static NcclApi g_nccl;
+
+static bool load_nccl() {
+    if (g_nccl.ok) return true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+#define SYM(field, name)                                                   \
+    *(void**)(&g_nccl.field) = dlsym(lib, name);                           \
+    if (!g_nccl.field) return false
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.ok = true;
+    return true;
+}
+
+#define REC_WORDS SPH_SLAB_RECORD_WORDS   // 24 x 4 B per migrating / ghost particle
+
+struct SlabState {
+    int rank = 0, world = 1;
+    int z_lo = 0, z_hi = 0;
+    ncclComm_t comm = nullptr;
+    // layout after the last sort
+    int own_begin = 0, own_end = 0;       // owned index range
+    int send_lo_n = 0, send_hi_n = 0;     // my boundary layers (== neighbours' ghost layers)
+    int ghost_lo_n = 0, ghost_hi_n = 0;
+    // exchange scratch
+    int* flags = nullptr;                 // cap ints
+    int* scan = nullptr;                  // cap + 1 ints
+    float* sendbuf[2] = {nullptr, nullptr};
+    float* recvbuf[2] = {nullptr, nullptr};
+    int buf_records = 0;
+    int* d_counts = nullptr;              // [0..1] send counts lo/hi, [2..3] recv counts lo/hi
+    int* h_ints = nullptr;                // pinned
+    int64_t halo_bytes = 0, halo_calls = 0;
+};
+
+namespace {
+
+int fail(SphHandle* h, int code, const char* msg) {
+    if (h) h->err = msg;
+    return code;
+}
+int nccl_check(SphHandle* h, int rc, const char* what) {
+    if (rc == ncclSuccess) return SPH_OK;
+    h->err = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "nccl error");
+    return SPH_E_CUDA;
+}
+#define NCCL_TRY(h, expr)                           \
+    do {                                            \
+        int _rc = nccl_check((h), (expr), #expr);   \
+        if (_rc) return _rc;                        \
+    } while (0)
+#define CU_TRY(h, expr)                                                         \
+    do {                                                                        \
+        cudaError_t _e = (expr);                                                \
+        if (_e != cudaSuccess) {                                                \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);      \
+            return SPH_E_CUDA;                                                  \
+        }                                                                       \
+    } while (0)
+
+// ghost_slot values
+enum { SLOT_OWNED = 0, SLOT_GHOST = 1, SLOT_DEAD = 2 };
+
+// mode 0 (migration): flag live owned particles whose cell layer left [z_lo, z_hi) towards `side`,
+//                     and retire every ghost and every leaver (SLOT_DEAD, dropped by the next sort)
+// mode 1 (ghost export): flag live owned particles of my boundary layer on `side`
+__global__ void __launch_bounds__(SPH_BLOCK) k_slab_flags(Consts c, Dev d, int mode, int side, int z_lo, int z_hi, int* flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    const int slot = d.ghost_slot[i];
+    const float4 p = d.pv[i];
+    const int cz = cell_of(c, p.x, p.y, p.z).z;
+    int f = 0;
+    if (mode == 0) {
+        if (slot == SLOT_OWNED) f = side == 0 ? (cz < z_lo) : (cz >= z_hi);
+    } else {
+        if (slot == SLOT_OWNED) f = side == 0 ? (cz == z_lo) : (cz == z_hi - 1);
+    }
+    flags[i] = f;
+}
+__global__ void __launch_bounds__(SPH_BLOCK) k_slab_retire(Consts c, Dev d, int z_lo, int z_hi) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N) return;
+    const int slot = d.ghost_slot[i];
+    if (slot == SLOT_GHOST) { d.ghost_slot[i] = SLOT_DEAD; return; }
+    if (slot != SLOT_OWNED) return;
+    const float4 p = d.pv[i];
+    const int cz = cell_of(c, p.x, p.y, p.z).z;
+    if (cz < z_lo || cz >= z_hi) d.ghost_slot[i] = SLOT_DEAD;
+}
+
+// full particle record: pv(4) vm(4) x0(3) rho(1) | object_id material is_dynamic uid color(3) pad
+__global__ void __launch_bounds__(SPH_BLOCK) k_slab_pack(Consts c, Dev d, const int* flags, const int* scan, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.N || !flags[i]) return;
+    float* r = out + (size_t)scan[i] * REC_WORDS;
+    int* ri = reinterpret_cast<int*>(r);
+    const float4 p = d.pv[i], v = d.vm[i];
+    r[0] = p.x; r[1] = p.y; r[2] = p.z; r[3] = p.w;
+    r[4] = v.x; r[5] = v.y; r[6] = v.z; r[7] = v.w;
+    r[8] = d.x0[3 * i]; r[9] = d.x0[3 * i + 1]; r[10] = d.x0[3 * i + 2];
+    r[11] = d.rho[i];
+    ri[12] = d.object_id[i]; ri[13] = d.material[i]; ri[14] = d.is_dynamic[i]; ri[15] = d.uid[i];
+    ri[16] = d.color[3 * i]; ri[17] = d.color[3 * i + 1]; ri[18] = d.color[3 * i + 2];
+    ri[19] = 0; ri[20] = 0; ri[21] = 0; ri[22] = 0; ri[23] = 0;
+}
+__global__ void __launch_bounds__(SPH_BLOCK) k_slab_unpack(Dev d, const float* in, int n, int base, int slot) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float* r = in + (size_t)k * REC_WORDS;
+    const int* ri = reinterpret_cast<const int*>(r);
+    const int i = base + k;
+    d.pv[i] = make_float4(r[0], r[1], r[2], r[3]);
+    d.vm[i] = make_float4(r[4], r[5], r[6], r[7]);
+    d.x0[3 * i] = r[8]; d.x0[3 * i + 1] = r[9]; d.x0[3 * i + 2] = r[10];
+    d.rho[i] = r[11];
+    d.object_id[i] = ri[12]; d.material[i] = ri[13]; d.is_dynamic[i] = ri[14]; d.uid[i] = ri[15];
+    d.color[3 * i] = ri[16]; d.color[3 * i + 1] = ri[17]; d.color[3 * i + 2] = ri[18];
+    d.ghost_slot[i] = slot;
+}
+
+int neighbour(const SlabState* s, int side) {
+    const int r = side == 0 ? s->rank - 1 : s->rank + 1;
+    return (r < 0 || r >= s->world) ? -1 : r;
+}
+
+// one phase of the pre-sort exchange: pack flagged particles per side, swap counts, swap records,
+// append what arrived with ghost_slot = slot
+int exchange_phase(SphHandle* h, int mode, int slot) {
+    SlabState* s = h->slab;
+    Consts& c = h->c;
+    const int nb = (c.N + SPH_BLOCK - 1) / SPH_BLOCK;
+    cudaStream_t st = h->stream;
+    CU_TRY(h, cudaMemsetAsync(s->d_counts, 0, 4 * sizeof(int), st));
+    for (int side = 0; side < 2; side++) {
+        if (neighbour(s, side) < 0 || c.N == 0) continue;
+        k_slab_flags<<<nb, SPH_BLOCK, 0, st>>>(c, h->d, mode, side, s->z_lo, s->z_hi, s->flags);
+        sph_exclusive_scan(h, s->flags, c.N, s->scan);
+        k_slab_pack<<<nb, SPH_BLOCK, 0, st>>>(c, h->d, s->flags, s->scan, s->sendbuf[side]);
+        CU_TRY(h, cudaMemcpyAsync(s->d_counts + side, s->scan + c.N, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        h->launches += 2;
+    }
+    // counts: device -> neighbours, then one host read of (send, recv) counts
+    NCCL_TRY(h, g_nccl.GroupStart());
+    for (int side = 0; side < 2; side++) {
+        const int nbr = neighbour(s, side);
+        if (nbr < 0) continue;
+        NCCL_TRY(h, g_nccl.Send(s->d_counts + side, 1, ncclInt32, nbr, s->comm, st));
+        NCCL_TRY(h, g_nccl.Recv(s->d_counts + 2 + side, 1, ncclInt32, nbr, s->comm, st));
+    }
+    NCCL_TRY(h, g_nccl.GroupEnd());
+    CU_TRY(h, cudaMemcpyAsync(s->h_ints, s->d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    const int send_n[2] = {s->h_ints[0], s->h_ints[1]}, recv_n[2] = {s->h_ints[2], s->h_ints[3]};
+    for (int side = 0; side < 2; side++)
+        if (send_n[side] > s->buf_records || recv_n[side] > s->buf_records)
+            return fail(h, SPH_E_CAPACITY, "slab exchange buffer too small");
+    if ((long long)c.N + recv_n[0] + recv_n[1] > c.cap) return fail(h, SPH_E_CAPACITY, "slab particle capacity exceeded by migration / ghosts");
+    NCCL_TRY(h, g_nccl.GroupStart());
+    for (int side = 0; side < 2; side++) {
+        const int nbr = neighbour(s, side);
+        if (nbr < 0) continue;
+        if (send_n[side] > 0) NCCL_TRY(h, g_nccl.Send(s->sendbuf[side], (size_t)send_n[side] * REC_WORDS, ncclFloat32, nbr, s->comm, st));
+        if (recv_n[side] > 0) NCCL_TRY(h, g_nccl.Recv(s->recvbuf[side], (size_t)recv_n[side] * REC_WORDS, ncclFloat32, nbr, s->comm, st));
+    }
+    NCCL_TRY(h, g_nccl.GroupEnd());
+    if (mode == 0 && c.N > 0) {   // leavers and the old ghosts die once the leavers are packed
+        k_slab_retire<<<nb, SPH_BLOCK, 0, st>>>(c, h->d, s->z_lo, s->z_hi);
+        h->launches++;
+    }
+    for (int side = 0; side < 2; side++) {
+        if (recv_n[side] <= 0) continue;
+        k_slab_unpack<<<(recv_n[side] + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, st>>>(h->d, s->recvbuf[side], recv_n[side], c.N, slot);
+        c.N += recv_n[side];
+        h->launches++;
+    }
+    s->halo_bytes += (int64_t)(send_n[0] + send_n[1]) * REC_WORDS * 4;
+    return cudaGetLastError() == cudaSuccess ? SPH_OK : fail(h, SPH_E_CUDA, cudaGetErrorString(cudaGetLastError()));
+}
+
+}  // namespace
+
+bool sph_is_slab(const SphHandle* h) { return h->slab != nullptr && h->slab->comm != nullptr; }
+
+// Migration + ghost re-import, run by the sort path right before the cell histogram.
+int sph_slab_pre_sort(SphHandle* h) {
+    int rc = exchange_phase(h, 0, SLOT_OWNED);
+    if (rc) return rc;
+    return exchange_phase(h, 1, SLOT_GHOST);
+}
+
+// After the scan: the live count and the layer boundaries (host needs them for launches / halos).
+int sph_slab_post_scan(SphHandle* h) {
+    SlabState* s = h->slab;
+    Consts& c = h->c;
+    const int plane = c.nx * c.ny;
+    const int z[6] = {s->z_lo - 1, s->z_lo, s->z_lo + 1, s->z_hi - 1, s->z_hi, s->z_hi + 1};
+    for (int k = 0; k < 6; k++) {
+        const int zz = z[k] < 0 ? 0 : (z[k] > c.nz ? c.nz : z[k]);
+        CU_TRY(h, cudaMemcpyAsync(s->h_ints + 8 + k, h->d.cell_start + (size_t)zz * plane, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU_TRY(h, cudaMemcpyAsync(s->h_ints + 14, h->d.cell_start + c.ncell, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    const int* v = s->h_ints + 8;
+    s->own_begin = v[1];
+    s->own_end = v[4];
+    s->ghost_lo_n = v[1] - v[0];
+    s->ghost_hi_n = v[5] - v[4];
+    s->send_lo_n = v[2] - v[1];
+    s->send_hi_n = v[4] - v[3];
+    if (neighbour(s, 0) < 0) { s->ghost_lo_n = 0; s->send_lo_n = 0; }
+    if (neighbour(s, 1) < 0) { s->ghost_hi_n = 0; s->send_hi_n = 0; }
+    c.N = s->h_ints[14];             // dead particles sit in the trash cell beyond the live ones
+    c.row_begin = s->own_begin;
+    c.row_end = s->own_end;
+    return SPH_OK;
+}
+
+// Refresh one field of my ghosts from its owners: contiguous ranges, element = elem_bytes.
+int sph_slab_halo(SphHandle* h, void* base, int elem_bytes) {
+    if (!sph_is_slab(h)) return SPH_OK;
+    SlabState* s = h->slab;
+    char* b = (char*)base;
+    const int lo = neighbour(s, 0), hi = neighbour(s, 1);
+    NCCL_TRY(h, g_nccl.GroupStart());
+    if (lo >= 0) {
+        if (s->send_lo_n > 0) NCCL_TRY(h, g_nccl.Send(b + (size_t)s->own_begin * elem_bytes, (size_t)s->send_lo_n * elem_bytes, ncclInt8, lo, s->comm, h->stream));
+        if (s->ghost_lo_n > 0) NCCL_TRY(h, g_nccl.Recv(b + (size_t)(s->own_begin - s->ghost_lo_n) * elem_bytes, (size_t)s->ghost_lo_n * elem_bytes, ncclInt8, lo, s->comm, h->stream));
+    }
+    if (hi >= 0) {
+        if (s->send_hi_n > 0) NCCL_TRY(h, g_nccl.Send(b + (size_t)(s->own_end - s->send_hi_n) * elem_bytes, (size_t)s->send_hi_n * elem_bytes, ncclInt8, hi, s->comm, h->stream));
+        if (s->ghost_hi_n > 0) NCCL_TRY(h, g_nccl.Recv(b + (size_t)s->own_end * elem_bytes, (size_t)s->ghost_hi_n * elem_bytes, ncclInt8, hi, s->comm, h->stream));
+    }
+    NCCL_TRY(h, g_nccl.GroupEnd());
+    s->halo_bytes += (int64_t)(s->send_lo_n + s->send_hi_n) * elem_bytes;
+    s->halo_calls++;
+    return SPH_OK;
+}
+
+// Sum a few doubles of Dev::red over all ranks (error sums of the solver loops).
+int sph_slab_allreduce_red(SphHandle* h, int slot, int count) {
+    if (!sph_is_slab(h)) return SPH_OK;
+    NCCL_TRY(h, g_nccl.AllReduce(h->d.red + slot, h->d.red + slot, (size_t)count, ncclFloat64, ncclSum, h->slab->comm, h->stream));
+    return SPH_OK;
+}
+
+void sph_slab_free(SphHandle* h) {
+    SlabState* s = h->slab;
+    if (!s) return;
+    if (s->comm && g_nccl.ok) g_nccl.CommDestroy(s->comm);
+    if (s->h_ints) cudaFreeHost(s->h_ints);
+    delete s;
+    h->slab = nullptr;
 }
 
 extern "C" {
-int sph_slab_set_range(SphHandle* h, int32_t, int32_t) { return unsupported(h); }
-int sph_slab_info(SphHandle* h, SphSlabInfo*) { return unsupported(h); }
-int sph_slab_begin_exchange(SphHandle* h, int32_t*) { return unsupported(h); }
-int sph_slab_pack(SphHandle* h, int32_t, int32_t, void**, int32_t*) { return unsupported(h); }
-int sph_slab_unpack(SphHandle* h, int32_t, int32_t, const void*, int32_t) { return unsupported(h); }
-int sph_slab_halo_pack(SphHandle* h, int32_t, int32_t, void**, int32_t*, int32_t*) { return unsupported(h); }
-int sph_slab_halo_unpack(SphHandle* h, int32_t, int32_t, const void*, int32_t) { return unsupported(h); }
-int sph_slab_halo_recv_count(SphHandle* h, int32_t, int32_t*) { return unsupported(h); }
+
+int sph_slab_unique_id(void* out128) {
+    if (!out128) return SPH_E_INVALID;
+    if (!load_nccl()) return SPH_E_UNSUPPORTED;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return SPH_E_CUDA;
+    memcpy(out128, &id, sizeof id);
+    return SPH_OK;
 }
+
+int sph_slab_init(SphHandle* h, int32_t rank, int32_t world, const void* unique_id128, int32_t z_lo, int32_t z_hi,
+                  int64_t global_particle_num) {
+    if (!h || !unique_id128 || world < 1 || rank < 0 || rank >= world) return SPH_E_INVALID;
+    if (!(h->P.flags & SPH_FLAG_SLAB)) return fail(h, SPH_E_STATE, "handle was not created with SPH_FLAG_SLAB");
+    if (z_lo < 0 || z_hi > h->c.nz || z_lo >= z_hi) return fail(h, SPH_E_INVALID, "bad slab range");
+    if (!load_nccl()) return fail(h, SPH_E_UNSUPPORTED, "libnccl.so.2 not found in the process");
+    if (h->slab) sph_slab_free(h);
+    SlabState* s = new SlabState();
+    h->slab = s;
+    s->rank = rank; s->world = world; s->z_lo = z_lo; s->z_hi = z_hi;
+    cudaSetDevice(h->P.device);
+    ncclUniqueId id;
+    memcpy(&id, unique_id128, sizeof id);
+    NCCL_TRY(h, g_nccl.CommInitRank(&s->comm, world, id, rank));
+    const size_t n = (size_t)h->c.cap;
+    // a boundary layer holds at most a few percent of a slab; size the exchange for a quarter of it
+    s->buf_records = (int)(n / 4 + 4096);
+    void* p = nullptr;
+#define DALLOC(ptr, bytes)                                     \
+    CU_TRY(h, cudaMalloc(&p, (bytes)));                        \
+    h->allocations.push_back(p);                               \
+    ptr = (decltype(ptr))p
+    DALLOC(s->flags, (n + 8) * sizeof(int));
+    DALLOC(s->scan, (n + 8) * sizeof(int));
+    for (int k = 0; k < 2; k++) {
+        DALLOC(s->sendbuf[k], (size_t)s->buf_records * REC_WORDS * 4);
+        DALLOC(s->recvbuf[k], (size_t)s->buf_records * REC_WORDS * 4);
+    }
+    DALLOC(s->d_counts, 8 * sizeof(int));
+#undef DALLOC
+    CU_TRY(h, cudaMallocHost((void**)&s->h_ints, 32 * sizeof(int)));
+    h->n_global = global_particle_num;
+    h->c.row_begin = 0;
+    h->c.row_end = h->c.N;
+    h->sorted_valid = false;
+    return SPH_OK;
+}
+
+int sph_slab_info(SphHandle* h, SphSlabInfo* out) {
+    if (!h || !out) return SPH_E_INVALID;
+    if (!h->slab) return fail(h, SPH_E_STATE, "not a slab handle");
+    SlabState* s = h->slab;
+    out->z_lo = s->z_lo; out->z_hi = s->z_hi;
+    out->n_owned = s->own_end - s->own_begin;
+    out->n_ghost = s->ghost_lo_n + s->ghost_hi_n;
+    out->n_send_lo = s->send_lo_n; out->n_send_hi = s->send_hi_n;
+    out->own_begin = s->own_begin; out->own_end = s->own_end;
+    out->halo_bytes = s->halo_bytes; out->halo_calls = s->halo_calls;
+    return SPH_OK;
+}
+
+int sph_slab_set_global_particle_num(SphHandle* h, int64_t n) {
+    if (!h) return SPH_E_INVALID;
+    h->n_global = n;
+    return SPH_OK;
+}
+
+}  // extern "C"

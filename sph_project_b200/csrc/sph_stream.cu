@@ -8,16 +8,20 @@ namespace {
 #define TID_OR_RETURN(n)                                   \
     const int i = blockIdx.x * blockDim.x + threadIdx.x;   \
     if (i >= (n)) return;
+// owned rows only (all particles unless the handle is a Z-slab)
+#define ROW_TID_OR_RETURN()                                \
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   \
+    SPH_ROW_OR_RETURN(c, i);
 
 // compute_gravity_acceleration (base_solver.py:202-207): assignment, fluid only
 __global__ void __launch_bounds__(SPH_BLOCK) k_gravity(Consts c, Dev d) {
-    TID_OR_RETURN(c.N);
+    ROW_TID_OR_RETURN();
     if (d.pv[i].w > 0.0f) d.acc[i] = make_float4(c.gx, c.gy, c.gz, 0.f);
 }
 
 // update_fluid_velocity (base_solver.py:642-649)
 __global__ void __launch_bounds__(SPH_BLOCK) k_update_velocity(Consts c, Dev d) {
-    TID_OR_RETURN(c.N);
+    ROW_TID_OR_RETURN();
     if (!(d.pv[i].w > 0.0f)) return;
     float4 v = d.vm[i];
     const float4 a = d.acc[i];
@@ -28,7 +32,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_update_velocity(Consts c, Dev d) 
 
 // update_fluid_position (base_solver.py:651-666) incl. the emitter branch
 __global__ void __launch_bounds__(SPH_BLOCK) k_update_position(Consts c, Dev d) {
-    TID_OR_RETURN(c.N);
+    ROW_TID_OR_RETURN();
     float4 p = d.pv[i];
     const float4 v = d.vm[i];
     if (p.w > 0.0f) {
@@ -50,7 +54,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_update_position(Consts c, Dev d) 
 
 // prepare_emitter (base_solver.py:669-677)
 __global__ void __launch_bounds__(SPH_BLOCK) k_prepare_emitter(Consts c, Dev d) {
-    TID_OR_RETURN(c.N);
+    ROW_TID_OR_RETURN();
     float4 p = d.pv[i];
     if (p.w > 0.0f && p.y > c.g_upper) {
         d.material[i] = SPH_MATERIAL_RIGID;
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_prepare_emitter(Consts c, Dev d) 
 
 // enforce_domain_boundary_3D + simulate_collisions (base_solver.py:544-605)
 __global__ void __launch_bounds__(SPH_BLOCK) k_boundary(Consts c, Dev d, int particle_type) {
-    TID_OR_RETURN(c.N);
+    ROW_TID_OR_RETURN();
     if (!(d.material[i] == particle_type && d.is_dynamic[i])) return;
     float4 p = d.pv[i];
     const float3 pos = f3(p);
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_boundary(Consts c, Dev d, int par
 
 // _renew_rigid_particle_state (base_solver.py:615-629)
 __global__ void __launch_bounds__(SPH_BLOCK) k_renew_rigid(Consts c, Dev d) {
-    TID_OR_RETURN(c.N);
+    ROW_TID_OR_RETURN();
     if (!(d.material[i] == SPH_MATERIAL_RIGID && d.is_dynamic[i])) return;
     const int obj = d.object_id[i];
     if (obj < 0 || obj >= SPH_MAX_OBJECTS || !d.rigid_is_dynamic[obj]) return;
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_renew_rigid(Consts c, Dev d) {
 
 // WCSPHSolver.compute_pressure (WCSPH.py:16-24): clamp written back, Tait EOS gamma = 7, B = 5e4
 __global__ void __launch_bounds__(SPH_BLOCK) k_wcsph_pressure(Consts c, Dev d) {
-    TID_OR_RETURN(c.N);
+    ROW_TID_OR_RETURN();
     if (!(d.pv[i].w > 0.0f)) return;
     const float rho = fmaxf(d.rho[i], c.rho0);
     d.rho[i] = rho;
@@ -114,11 +118,11 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_wcsph_pressure(Consts c, Dev d) {
 
 // DFSPH compute_kappa_v (DFSPH.py:132-137) / compute_kappa (:217-223)
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_kappa_v(Consts c, Dev d) {
-    TID_OR_RETURN(c.N);
+    ROW_TID_OR_RETURN();
     if (d.pv[i].w > 0.0f) d.kappa_v[i] = d.drho[i] * d.alpha[i];
 }
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_kappa(Consts c, Dev d) {
-    TID_OR_RETURN(c.N);
+    ROW_TID_OR_RETURN();
     if (d.pv[i].w > 0.0f) d.kappa[i] = (d.rho_star[i] - 1.0f) * d.alpha[i] * c.inv_dt;
 }
 
@@ -128,7 +132,7 @@ template <bool DIVERGENCE>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_error(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float e = 0.0f;
-    if (i < c.N && d.pv[i].w > 0.0f) e = DIVERGENCE ? c.rho0 * d.drho[i] : d.rho_star[i] - 1.0f;
+    if (SPH_IS_ROW(c, i) && d.pv[i].w > 0.0f) e = DIVERGENCE ? c.rho0 * d.drho[i] : d.rho_star[i] - 1.0f;
     block_reduce_add(d.red + RED_ERR, (double)e);
 }
 
@@ -346,12 +350,12 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_ref_cell_hist(Consts c, Dev d, in
     } while (0)
 
 void sph_launch_gravity(SphHandle* h) { LAUNCH_N(k_gravity, h->c.N, h->c, h->d); }
-void sph_launch_update_velocity(SphHandle* h) { LAUNCH_N(k_update_velocity, h->c.N, h->c, h->d); }
-void sph_launch_update_position(SphHandle* h) { LAUNCH_N(k_update_position, h->c.N, h->c, h->d); h->list_valid = false; h->rec_pos_valid = false; }
-void sph_launch_boundary(SphHandle* h, int t) { LAUNCH_N(k_boundary, h->c.N, h->c, h->d, t); h->list_valid = false; h->rec_pos_valid = false; h->rec_vel_valid = false; }
+void sph_launch_update_velocity(SphHandle* h) { LAUNCH_N(k_update_velocity, h->c.N, h->c, h->d); sph_ghost_dirty(h, GHOST_VEL); }
+void sph_launch_update_position(SphHandle* h) { LAUNCH_N(k_update_position, h->c.N, h->c, h->d); h->list_valid = false; h->rec_pos_valid = false; sph_ghost_dirty(h, GHOST_PV); }
+void sph_launch_boundary(SphHandle* h, int t) { LAUNCH_N(k_boundary, h->c.N, h->c, h->d, t); h->list_valid = false; h->rec_pos_valid = false; h->rec_vel_valid = false; sph_ghost_dirty(h, GHOST_PV | GHOST_VEL); }
 void sph_launch_renew_rigid(SphHandle* h) { LAUNCH_N(k_renew_rigid, h->c.N, h->c, h->d); h->list_valid = false; h->rec_pos_valid = false; h->rec_vel_valid = false; }
 void sph_launch_prepare_emitter(SphHandle* h) { LAUNCH_N(k_prepare_emitter, h->c.N, h->c, h->d); h->list_valid = false; h->rec_pos_valid = false; }
-void sph_launch_wcsph_pressure(SphHandle* h) { LAUNCH_N(k_wcsph_pressure, h->c.N, h->c, h->d); }
+void sph_launch_wcsph_pressure(SphHandle* h) { LAUNCH_N(k_wcsph_pressure, h->c.N, h->c, h->d); sph_ghost_dirty(h, GHOST_RHO); }
 void sph_launch_dfsph_kappa_v(SphHandle* h) { LAUNCH_N(k_dfsph_kappa_v, h->c.N, h->c, h->d); }
 void sph_launch_dfsph_kappa(SphHandle* h) { LAUNCH_N(k_dfsph_kappa, h->c.N, h->c, h->d); }
 void sph_launch_dfsph_divergence_error(SphHandle* h) { LAUNCH_N(k_dfsph_error<true>, h->c.N, h->c, h->d); }

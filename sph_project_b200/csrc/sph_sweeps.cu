@@ -128,14 +128,15 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_sync_records(Consts c, Dev d, int
     const float4 p = d.pv[i];
     d.recA[i].lo = p;
     d.recB[i].lo = p;
-    if (with_vel) d.recA[i].hi = d.vm[i];
+    // ghost velocities live in recA only (refreshed by halos), never re-derived from the ghosts' vm
+    if (with_vel && SPH_IS_ROW(c, i)) d.recA[i].hi = d.vm[i];
 }
 
 // compute_rigid_particle_volume (base_solver.py:105-123); rigid rows, plain window walk in global
 // memory (once per step over the boundary shell)
 __global__ void __launch_bounds__(SPH_BLOCK) k_rigid_volume(Consts c, Dev d) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
+    SPH_ROW_OR_RETURN(c, i);
     float4 pi = d.pv[i];
     if (!(pi.w < 0.0f) || !(pi.y <= c.g_upper)) return;
     const int obj_i = d.object_id[i];
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_density(Consts c, Dev d, int wmax
     __shared__ unsigned long long s_mbar;
     const Window win = window_open(d, dyn_smem, wmax, s_desc, &s_mbar);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
+    SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
     if (!(pi.w > 0.0f)) {
         if (BUILD) d.nbr_count[i] = 0;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_density(Consts c, Dev d, int wmax
 template <bool TEMP, bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_pressure_accel(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
+    SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
     float4* out = TEMP ? d.a_p : d.acc;
     bool active = pi.w > 0.0f;
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_pressure_accel(Consts c, Dev d) {
 template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_surface_tension(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
+    SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
     if (!(pi.w > 0.0f)) return;
     const float sm = c.sigma / d.recB[i].hi.w;
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_surface_tension(Consts c, Dev d) 
 template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_viscosity(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
+    SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
     if (!(pi.w > 0.0f)) return;
     const float4 vi = d.vm[i];
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_viscosity(Consts c, Dev d) {
 template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_alpha(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
+    SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
     if (!(pi.w > 0.0f)) return;
     float3 grad_i = make_float3(0.f, 0.f, 0.f);
@@ -295,7 +296,7 @@ template <bool STAR, bool LIST, bool FUSED>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float err = 0.0f;
-    if (i < c.N) {
+    if (SPH_IS_ROW(c, i)) {
         const float4 pi = d.pv[i];
         if (pi.w > 0.0f) {
             const float4 vi = d.vm[i];
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, De
 template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_correct(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
+    SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
     if (!(pi.w > 0.0f)) return;
     const float4 ai = d.recB[i].hi;
@@ -366,7 +367,7 @@ template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_pcisph_density_star(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float err = 0.0f;
-    if (i < c.N) {
+    if (SPH_IS_ROW(c, i)) {
         const float4 pi = d.pv[i];
         if (pi.w > 0.0f) {
             const float4 xi = d.x_pred[i];
@@ -398,7 +399,7 @@ __device__ __forceinline__ float visc_A_scale(const Consts& c, float mi, float d
 template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_cg_prepare1(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
+    SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
     if (!(pi.w > 0.0f)) return;
     const float4 vi = d.vm[i];
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_cg_prepare1(Consts c, Dev d) {
 template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_cg_Ap(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
+    SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
     if (!(pi.w > 0.0f)) return;
     const float4 ai = d.recB[i].hi;
@@ -525,14 +526,33 @@ static void ensure_records(SphHandle* h, bool need_vel) {
     if (h->rec_pos_valid && (!need_vel || h->rec_vel_valid)) return;
     if (h->c.N > 0) {
         SphProf _prof(h, "k_sync_records");
-        k_sync_records<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d, 1);
+        const int with_vel = !h->rec_vel_valid;
+        k_sync_records<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d, with_vel);
         h->launches++;
+        if (with_vel) sph_ghost_dirty(h, GHOST_VEL);
     }
     h->rec_pos_valid = true;
     h->rec_vel_valid = true;
 }
 
+// refresh ghost copies that lag their owners (Z-slabs): contiguous NCCL halo of each stale field
+void sph_ghost_sync(SphHandle* h, int what) {
+    if (!sph_is_slab(h)) return;
+    const int need = h->ghost_stale & what;
+    int rc = 0;
+    if (!rc && (need & GHOST_PV)) {
+        rc = sph_slab_halo(h, h->d.pv, 16);
+        h->rec_pos_valid = false;   // record copies of the ghosts' pv are refreshed by ensure_records
+    }
+    if (!rc && (need & GHOST_RHO)) rc = sph_slab_halo(h, h->d.rho, 4);
+    if (!rc && (need & GHOST_VEL)) rc = sph_slab_halo(h, h->d.recA, 32);
+    if (!rc && (need & GHOST_AUX)) rc = sph_slab_halo(h, h->d.recB, 32);
+    if (rc && !h->sticky_rc) h->sticky_rc = rc;
+    h->ghost_stale &= ~need;
+}
+
 static void prep_aux(SphHandle* h, int mode) {
+    sph_ghost_dirty(h, GHOST_AUX);
     switch (mode) {
         case AUX_RHO_M: LAUNCH(k_prep_aux<AUX_RHO_M>); break;
         case AUX_KAPPA: LAUNCH(k_prep_aux<AUX_KAPPA>); break;
@@ -541,8 +561,10 @@ static void prep_aux(SphHandle* h, int mode) {
     }
 }
 
-void sph_launch_rigid_volume(SphHandle* h) { LAUNCH(k_rigid_volume); }
+void sph_launch_rigid_volume(SphHandle* h) { LAUNCH(k_rigid_volume); sph_ghost_dirty(h, GHOST_PV); }
 void sph_launch_density(SphHandle* h) {
+    sph_ghost_sync(h, GHOST_PV);
+    sph_ghost_dirty(h, GHOST_RHO);
     if (h->lists_enabled) {
         LAUNCH_WIN(k_density<true, true>);
         h->list_valid = true;
@@ -550,31 +572,49 @@ void sph_launch_density(SphHandle* h) {
         LAUNCH_WIN(k_density<true, false>);
     }
 }
-void sph_launch_pressure_accel(SphHandle* h) { ensure_records(h, false); prep_aux(h, AUX_PRESSURE); LAUNCH_LIST(k_pressure_accel, false, ); }
-void sph_launch_temp_pressure_accel(SphHandle* h) { ensure_records(h, false); prep_aux(h, AUX_PRESSURE); LAUNCH_LIST(k_pressure_accel, true, ); }
-void sph_launch_surface_tension(SphHandle* h) { ensure_records(h, false); prep_aux(h, AUX_RHO_M); LAUNCH_LIST(k_surface_tension, ); }
-void sph_launch_viscosity(SphHandle* h, bool) { ensure_records(h, true); LAUNCH_LIST(k_viscosity, ); }
-void sph_launch_dfsph_alpha(SphHandle* h) { LAUNCH_LIST(k_dfsph_alpha, ); }
+void sph_launch_pressure_accel(SphHandle* h) { sph_ghost_sync(h, GHOST_PV); ensure_records(h, false); prep_aux(h, AUX_PRESSURE); sph_ghost_sync(h, GHOST_AUX); LAUNCH_LIST(k_pressure_accel, false, ); }
+void sph_launch_temp_pressure_accel(SphHandle* h) { sph_ghost_sync(h, GHOST_PV); ensure_records(h, false); prep_aux(h, AUX_PRESSURE); sph_ghost_sync(h, GHOST_AUX); LAUNCH_LIST(k_pressure_accel, true, ); }
+void sph_launch_surface_tension(SphHandle* h) {
+    sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
+    ensure_records(h, false);
+    prep_aux(h, AUX_RHO_M);
+    h->ghost_stale &= ~GHOST_AUX;   // the ghosts' (rho, m) are local data: nothing to fetch
+    LAUNCH_LIST(k_surface_tension, );
+}
+void sph_launch_viscosity(SphHandle* h, bool) { sph_ghost_sync(h, GHOST_PV | GHOST_RHO); ensure_records(h, true); sph_ghost_sync(h, GHOST_VEL); LAUNCH_LIST(k_viscosity, ); }
+void sph_launch_dfsph_alpha(SphHandle* h) { sph_ghost_sync(h, GHOST_PV); LAUNCH_LIST(k_dfsph_alpha, ); }
 void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused) {
+    sph_ghost_sync(h, GHOST_PV);
     ensure_records(h, true);
+    sph_ghost_sync(h, GHOST_VEL);
+    if (fused) sph_ghost_dirty(h, GHOST_AUX);
     if (sph_lists_ready(h)) { if (fused) LAUNCH(k_dfsph_density_change<false, true, true>); else LAUNCH(k_dfsph_density_change<false, true, false>); }
     else { if (fused) LAUNCH(k_dfsph_density_change<false, false, true>); else LAUNCH(k_dfsph_density_change<false, false, false>); }
 }
 void sph_launch_dfsph_density_star(SphHandle* h, bool fused) {
+    sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
     ensure_records(h, true);
+    sph_ghost_sync(h, GHOST_VEL);
+    if (fused) sph_ghost_dirty(h, GHOST_AUX);
     if (sph_lists_ready(h)) { if (fused) LAUNCH(k_dfsph_density_change<true, true, true>); else LAUNCH(k_dfsph_density_change<true, true, false>); }
     else { if (fused) LAUNCH(k_dfsph_density_change<true, false, true>); else LAUNCH(k_dfsph_density_change<true, false, false>); }
 }
 // aux_ready: the fused density-change kernel has just written recB.hi = (kappa, kappa/rho, rho, m)
 void sph_launch_dfsph_correct_divergence(SphHandle* h, bool aux_ready) {
+    sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
     ensure_records(h, false);
     if (!aux_ready) prep_aux(h, AUX_KAPPA_V);
+    sph_ghost_sync(h, GHOST_AUX);
     LAUNCH_LIST(k_dfsph_correct, );
+    sph_ghost_dirty(h, GHOST_VEL);
 }
 void sph_launch_dfsph_correct_density(SphHandle* h, bool aux_ready) {
+    sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
     ensure_records(h, false);
     if (!aux_ready) prep_aux(h, AUX_KAPPA);
+    sph_ghost_sync(h, GHOST_AUX);
     LAUNCH_LIST(k_dfsph_correct, );
+    sph_ghost_dirty(h, GHOST_VEL);
 }
 void sph_launch_pcisph_density_star(SphHandle* h) { LAUNCH_LIST(k_pcisph_density_star, ); }
 void sph_launch_cg_prepare1(SphHandle* h) { ensure_records(h, true); LAUNCH_LIST(k_cg_prepare1, ); }

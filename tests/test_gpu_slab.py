@@ -1,0 +1,30 @@
+"""Z-slab (multi-GPU) parity: needs >= 2 GPUs on the box; spawns tests/slab_check.py under torchrun."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+from helpers import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpus():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("method", ["dfsph", "wcsph"])
+def test_two_slabs_match_single_gpu(method):
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, SLAB_CHECK_METHOD=method, SLAB_CHECK_STEPS="30")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531", os.path.join(ROOT, "tests", "slab_check.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert out.returncode == 0 and lines, out.stdout[-2000:] + out.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert res["ok"] and res["conserved"] and res["max_rel_position_error"] < 1e-4, res

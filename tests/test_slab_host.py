@@ -1,0 +1,90 @@
+"""Host-side logic of the Z-slab path on CPU: slab ranges, ownership, and the torch.distributed
+plumbing over the gloo backend with world_size 2 (the NCCL data path itself needs GPUs)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, scene
+from sph_project_b200.slab import SlabContext, balanced_ranges, cell_layer
+
+
+def test_balanced_ranges_cover_and_balance():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 4, 8):
+        counts = rng.integers(0, 5000, size=50)
+        r = balanced_ranges(counts, world)
+        assert r[0][0] == 0 and r[-1][1] == 50
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert all(hi - lo >= 2 for lo, hi in r)
+        loads = [counts[lo:hi].sum() for lo, hi in r]
+        assert max(loads) <= counts.sum() / world + 2 * counts.max()
+    with pytest.raises(ValueError):
+        balanced_ranges([1, 1, 1], 2)
+
+
+def test_uniform_block_splits_evenly():
+    counts = [0, 0] + [1000] * 40 + [0, 0]
+    r = balanced_ranges(counts, 4)
+    assert [counts[lo:hi].__len__() for lo, hi in r] and [sum(counts[lo:hi]) for lo, hi in r] == [10000] * 4
+
+
+def test_ownership_is_a_partition():
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0, 2.0, size=(20000, 3)).astype(np.float32)
+    nz = 50
+    counts = np.bincount(cell_layer(x[:, 2], 0.04, nz), minlength=nz)
+    ranges = balanced_ranges(counts, 4)
+    owned = np.stack([SlabContext(r, 4, 0.04, nz, ranges).owned(x) for r in range(4)])
+    assert np.all(owned.sum(0) == 1)
+    for r in range(4):
+        ctx = SlabContext(r, 4, 0.04, nz, ranges)
+        lo, hi = max(ctx.z_lo - 1, 0), min(ctx.z_hi + 1, nz)
+        assert ctx.capacity(counts) >= counts[lo:hi].sum()
+
+
+def test_cell_layer_matches_device_arithmetic():
+    z = np.array([0.0, 0.0399999, 0.04, 0.07999999, 0.08, 1.9999999, 2.5], dtype=np.float32)
+    expect = np.clip((z / np.float32(0.04)).astype(np.int64), 0, 49)
+    assert np.array_equal(cell_layer(z, 0.04, 50), expect)
+
+
+WORKER = textwrap.dedent("""
+    import os, sys, json
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+    import numpy as np, torch.distributed as dist
+    from helpers import scene
+    from sph_project_b200.slab import SlabContext, balanced_ranges, cell_layer, broadcast_bytes
+    from sph_project_b200.containers.base_container import _lattice
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    # the 128-byte id rank 0 would get from ncclGetUniqueId
+    uid = bytes(range(128)) if rank == 0 else None
+    got = broadcast_bytes(uid, 128, src=0)
+    assert got == bytes(range(128))
+    # every rank derives the same slab ranges from the same scene and owns a disjoint share
+    pos = _lattice([0.1, 0.1, 0.1], [0.2, 0.4, 1.0], 0.02, 3)
+    nz = 30
+    counts = np.bincount(cell_layer(pos[:, 2], 0.04, nz), minlength=nz)
+    ctx = SlabContext(rank, world, 0.04, nz, balanced_ranges(counts, world))
+    mine = int(ctx.owned(pos).sum())
+    out = [None] * world
+    dist.all_gather_object(out, (ctx.ranges, mine))
+    assert all(o[0] == out[0][0] for o in out)
+    assert sum(o[1] for o in out) == pos.shape[0]
+    assert abs(out[0][1] - out[1][1]) <= counts.max()
+    dist.destroy_process_group()
+    print("WORKER_OK", rank)
+""")
+
+
+def test_gloo_world_size_2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29517", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert out.returncode == 0 and out.stdout.count("WORKER_OK") == 2, out.stdout[-1500:] + out.stderr[-3000:]
