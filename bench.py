@@ -64,8 +64,9 @@ def algo_bytes(kernel, n_total, n_pairs):
 
 def dam_break_scene(method="dfsph", scale=1.0, n_slabs=1):
     """final_scene0.json geometry (reference data/scenes/final_scene0.json:5-16,52-63), no RigidBodies.
-    scale < 1 shrinks every length (bounded CPU sample); n_slabs > 1 stretches z (weak scaling)."""
-    z = 2.0 * scale * n_slabs
+    scale < 1 shrinks every length (bounded CPU sample); n_slabs > 1 stretches the block and the
+    domain along z by 1.6 m (80 particle layers = 1,231,200 fluid particles) per extra slab (weak scaling)."""
+    z = (1.6 * n_slabs + 0.4) * scale
     cfg = {
         "domainStart": [0.0, 0.0, 0.0], "domainEnd": [8.5 * scale, 8.0 * scale, z], "particleRadius": 0.01,
         "addDomainBox": True, "density0": 1000, "gravitation": [0.0, -9.81, 0.0], "simulationMethod": method,
@@ -226,6 +227,9 @@ def run_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (the product has no CPU path)")
+    # stdout carries exactly one JSON line: park fd 1 on stderr while libraries (NCCL banner) may print
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -381,7 +385,12 @@ def run_gpu(args, rank, world, local_rank):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(stats.kernel_launches),
             "clocks": clock_info, "setup_s": time.perf_counter() - t_setup,
         }
-        print(json.dumps(line), flush=True)
+        if world > 1:
+            info = eng.slab_info()
+            line["config"]["slab"] = {"layers_rank0": [info.z_lo, info.z_hi], "owned_rank0": info.n_owned, "ghosts_rank0": info.n_ghost,
+                                      "halo_refreshes_rank0": int(info.halo_calls), "bytes_sent_rank0": int(info.halo_bytes),
+                                      "transport": "NCCL send/recv + allreduce over NVLink, issued by the library on its stream"}
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
