@@ -48,20 +48,17 @@ LIST_CONSUMERS = ("k_dfsph_alpha", "k_dfsph_density_change", "k_dfsph_correct", 
 
 def algo_bytes(kernel, n_total, n_pairs):
     """Algorithmic bytes of one launch: the SURVEY 8(d) per-particle figure x all particles, plus the
-    neighbour list itself (4 B per accepted pair; 16 B with the DFSPH pair geometry) for the kernel that writes it (k_density<.., true>)
+    neighbour list itself (4 B per accepted pair) for the kernel that writes it (k_density<.., true>)
     and for the kernels that stream it instead of re-deriving it from positions."""
     base = kernel.split("<")[0]
     if base not in ALGO_BYTES:
         return None
     b = ALGO_BYTES[base] * n_total
     args = kernel.replace(" ", "")
-    if base == "k_density":
-        targs = args[args.index("<") + 1:-1].split(",")
-        if len(targs) >= 2 and targs[1] == "true":          # list build: index list (+ pair geometry)
-            b += (20 if len(targs) >= 3 and targs[2] == "true" else 4) * n_pairs + 4 * n_total
+    if base == "k_density" and args.endswith(",true>"):
+        b += 4 * n_pairs + 4 * n_total
     if base in LIST_CONSUMERS and args.endswith("true>") and not (base == "k_dfsph_density_change" and args.endswith(",false,true>")):
-        # DFSPH iteration kernels stream {g_ij, j} (16 B per pair); the others the 4-byte index list
-        b += (16 if base.startswith("k_dfsph") else 4) * n_pairs
+        b += 4 * n_pairs
     return b
 
 

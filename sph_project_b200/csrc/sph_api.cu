@@ -430,8 +430,6 @@ int sph_create(const SphParams* p, SphHandle** out) {
         ALLOC(d.win_stats, 4);
         ALLOC(d.recA, n);
         ALLOC(d.recB, n);
-        ALLOC(d.aux2, n);
-        if (h->lists_enabled && p->method == SPH_METHOD_DFSPH) { ALLOC(d.pairg, (size_t)d.nbr_kmax * (size_t)d.nbr_stride); }
         const char* w = getenv("SPH_B200_WMAX");   // window slots per CTA (16 B x payload arrays each)
         h->wmax = w ? atoi(w) : 1536;
         if (h->wmax < 64) h->wmax = 64;

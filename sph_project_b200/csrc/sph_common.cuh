@@ -100,10 +100,6 @@ struct Dev {
     //                                              DFSPH correction, (p/rho^2, p) for the pressure force
     Rec* recA;
     Rec* recB;
-    // DFSPH: pair geometry {V_j grad W_ij, j or ~j} per accepted pair, same ELL layout as nbr, and
-    // aux2[j] = (kappa_j, kappa_j / rho_j); both streamed / gathered by the solver-iteration kernels
-    float4* pairg;
-    float2* aux2;
 };
 
 // one 256-bit read-only gather of a neighbour record

@@ -102,49 +102,6 @@ __device__ __forceinline__ void pv_neighbors(const Consts& c, const Dev& d, int 
     for_all_neighbors(c, d, i, pi, visit);
 }
 
-// DFSPH iteration kernels: the pair geometry g_ij = V_j grad W_ij is constant while positions are
-// frozen, so the list build stores it once ({g_ij, j} = 16 B per pair, j complemented for non-fluid
-// neighbours) and the ~50 correction / density-change sweeps per step stream it (coalesced LDG.128)
-// instead of re-gathering positions and re-evaluating the kernel gradient.  visit(j, fluid_j, g).
-template <bool LIST, class Visit>
-__device__ __forceinline__ void geom_neighbors(const Consts& c, const Dev& d, int i, float4 pi, Visit&& visit) {
-    if (LIST) {
-        const int n = d.nbr_count[i];
-        if (n <= d.nbr_kmax) {
-            const float4* __restrict__ col = d.pairg + i;
-            const size_t stride = (size_t)d.nbr_stride;
-            int k = 0;
-            for (; k + 4 <= n; k += 4) {
-                const float4 q0 = __ldg(col + (size_t)k * stride), q1 = __ldg(col + (size_t)(k + 1) * stride);
-                const float4 q2 = __ldg(col + (size_t)(k + 2) * stride), q3 = __ldg(col + (size_t)(k + 3) * stride);
-                int j;
-                j = __float_as_int(q0.w); visit(j < 0 ? ~j : j, j >= 0, make_float3(q0.x, q0.y, q0.z));
-                j = __float_as_int(q1.w); visit(j < 0 ? ~j : j, j >= 0, make_float3(q1.x, q1.y, q1.z));
-                j = __float_as_int(q2.w); visit(j < 0 ? ~j : j, j >= 0, make_float3(q2.x, q2.y, q2.z));
-                j = __float_as_int(q3.w); visit(j < 0 ? ~j : j, j >= 0, make_float3(q3.x, q3.y, q3.z));
-            }
-            for (; k < n; k++) {
-                const float4 q = __ldg(col + (size_t)k * stride);
-                const int j = __float_as_int(q.w);
-                visit(j < 0 ? ~j : j, j >= 0, make_float3(q.x, q.y, q.z));
-            }
-            return;
-        }
-    }
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
-        visit(j, pj.w > 0.0f, R * (fabsf(pj.w) * kernel_gradient_scale(c, r2)));
-    });
-}
-
-// aux2[i] = (kappa_i, kappa_i / rho_i): what the DFSPH correction step gathers about a fluid neighbour
-template <bool DIVERGENCE>
-__global__ void __launch_bounds__(SPH_BLOCK) k_prep_aux2(Consts c, Dev d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
-    const float k = DIVERGENCE ? d.kappa_v[i] : d.kappa[i];
-    d.aux2[i] = make_float2(k, k / d.rho[i]);
-}
-
 // recB[i].hi = (s0, s1, rho_i, m_i), the scalar payload of the pressure / correction / tension sweeps
 enum AuxMode { AUX_RHO_M, AUX_KAPPA, AUX_KAPPA_V, AUX_PRESSURE };
 template <int MODE>
@@ -171,7 +128,8 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_sync_records(Consts c, Dev d, int
     const float4 p = d.pv[i];
     d.recA[i].lo = p;
     d.recB[i].lo = p;
-    if (with_vel) d.recA[i].hi = d.vm[i];
+    // ghost velocities live in recA only (refreshed by halos), never re-derived from the ghosts' vm
+    if (with_vel && SPH_IS_ROW(c, i)) d.recA[i].hi = d.vm[i];
 }
 
 // compute_rigid_particle_volume (base_solver.py:105-123); rigid rows, plain window walk in global
@@ -196,8 +154,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_rigid_volume(Consts c, Dev d) {
 
 // compute_density (base_solver.py:521-541) fused with the neighbour-list build; candidates come
 // from the TMA-staged window.  DENSITY: write rho; BUILD: record the accepted neighbours.
-// GEOM: also the pair geometry {V_j grad W_ij, j} streamed by the DFSPH iteration kernels.
-template <bool DENSITY, bool BUILD, bool GEOM>
+template <bool DENSITY, bool BUILD>
 __global__ void __launch_bounds__(SPH_BLOCK) k_density(Consts c, Dev d, int wmax) {
     __shared__ int s_desc[SPH_DESC_INTS];
     __shared__ unsigned long long s_mbar;
@@ -212,19 +169,12 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_density(Consts c, Dev d, int wmax
     float ret = 0.0f;
     int n = 0;
     int* col = d.nbr + i;
-    float4* gcol = d.pairg + i;
     const size_t stride = (size_t)d.nbr_stride;
     const int kmax = d.nbr_kmax;
-    auto body = [&](int j, float4 pj, float3 R, float r2) {
+    auto body = [&](int j, float4 pj, float3, float r2) {
         if (DENSITY) ret += fabsf(pj.w) * kernel_W_q(c, sqrtf(r2) * c.inv_h);
         if (BUILD) {
-            if (n < kmax) {
-                col[(size_t)n * stride] = j;
-                if (GEOM) {
-                    const float s = fabsf(pj.w) * kernel_gradient_scale(c, r2);
-                    gcol[(size_t)n * stride] = make_float4(R.x * s, R.y * s, R.z * s, __int_as_float(pj.w > 0.0f ? j : ~j));
-                }
-            }
+            if (n < kmax) col[(size_t)n * stride] = j;
             n++;
         }
     };
@@ -319,7 +269,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_viscosity(Consts c, Dev d) {
     d.acc[i] = make_float4(acc.x + a.x * c.inv_rho0, acc.y + a.y * c.inv_rho0, acc.z + a.z * c.inv_rho0, 0.f);
 }
 
-// DFSPH compute_alpha (DFSPH.py:22-62): g_j = -V_j grad W_ij
+// DFSPH compute_alpha (DFSPH.py:22-62)
 template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_alpha(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -328,18 +278,19 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_alpha(Consts c, Dev d) {
     if (!(pi.w > 0.0f)) return;
     float3 grad_i = make_float3(0.f, 0.f, 0.f);
     float sum_k = 0.0f;
-    geom_neighbors<LIST>(c, d, i, pi, [&](int, bool fluid_j, float3 g) {
-        if (fluid_j) sum_k += dist2(g);
-        grad_i = grad_i - g;
+    pv_neighbors<LIST>(c, d, i, pi, [&](int, float4 pj, float3 R, float r2) {
+        const float s = -fabsf(pj.w) * kernel_gradient_scale(c, r2);
+        const float3 g = R * s;
+        if (pj.w > 0.0f) sum_k += dist2(g);
+        grad_i = grad_i + g;
     });
     sum_k += dist2(grad_i);
     d.alpha[i] = sum_k > 1e-5f ? 1.0f / sum_k : 0.0f;
 }
 
-// DFSPH compute_density_derivative (DFSPH.py:65-101) / compute_density_star (:104-126):
-// sum_j (v_i - v_j) . g_ij; one 16-byte gather (v_j) per pair.
+// DFSPH compute_density_derivative (DFSPH.py:65-101) / compute_density_star (:104-126).
 // FUSED (the library's own solver loops): also the kappa of the next correction step
-// (compute_kappa_v :132-137 / compute_kappa :217-223, written to the field and to aux2) and the
+// (compute_kappa_v :132-137 / compute_kappa :217-223, written to the field and to recB.hi) and the
 // error sum (compute_density_derivative_error :205-211 / compute_density_error :285-294).
 template <bool STAR, bool LIST, bool FUSED>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, Dev d) {
@@ -351,9 +302,9 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, De
             const float4 vi = d.vm[i];
             float delta = 0.0f;
             int nn = 0;
-            geom_neighbors<LIST>(c, d, i, pi, [&](int j, bool, float3 g) {
-                const float4 vj = __ldg(d.vm + j);
-                delta += dot3(make_float3(vi.x - vj.x, vi.y - vj.y, vi.z - vj.z), g);
+            rec_neighbors<LIST>(c, d, d.recA, i, pi, [&](int, float4 pj, float4 vj, float3 R, float r2) {
+                const float vr = dot3(make_float3(vi.x - vj.x, vi.y - vj.y, vi.z - vj.z), R);
+                delta = fmaf(fabsf(pj.w) * kernel_gradient_scale(c, r2), vr, delta);
                 nn++;
             });
             const float rho = d.rho[i];
@@ -370,40 +321,39 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, De
                 kap = adv * d.alpha[i];
                 if (FUSED) { d.kappa_v[i] = kap; err = c.rho0 * adv; }
             }
-            if (FUSED) d.aux2[i] = make_float2(kap, kap / rho);
+            if (FUSED) d.recB[i].hi = make_float4(kap, kap / rho, rho, vi.w);
         }
     }
     if (FUSED) block_reduce_add(d.red + RED_ERR, (double)err);
 }
 
-// DFSPH correct_divergence_step (DFSPH.py:161-202) / correct_density_error_step (:245-283):
-// v_i -= g_ij (kappa_i/rho_i + kappa_j/rho_j) rho0; one 8-byte gather (aux2_j) per fluid pair.
+// DFSPH correct_divergence_step (DFSPH.py:161-202) / correct_density_error_step (:245-283).
+// recB.hi = (kappa_j, kappa_j / rho_j, rho_j, m_j); the new velocity goes to vm and to recA.hi
 template <bool LIST>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_correct(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
     if (!(pi.w > 0.0f)) return;
-    const float2 ai = d.aux2[i];
+    const float4 ai = d.recB[i].hi;
     const float k_i = ai.x, ki_rho = ai.y;
     const float thresh = 1e-5f * c.dt;   // m_eps * dt
     const bool rigid_on = fabsf(k_i) > thresh;
     float3 dv = make_float3(0.f, 0.f, 0.f);
-    geom_neighbors<LIST>(c, d, i, pi, [&](int j, bool fluid_j, float3 g) {
+    rec_neighbors<LIST>(c, d, d.recB, i, pi, [&](int j, float4 pj, float4 aj, float3 R, float r2) {
         float s;
-        if (fluid_j) {
-            const float2 aj = __ldg(d.aux2 + j);
+        if (pj.w > 0.0f) {
             if (!(fabsf(k_i + aj.x) > thresh)) return;
-            s = (ki_rho + aj.y) * c.rho0;
+            s = pj.w * kernel_gradient_scale(c, r2) * (ki_rho + aj.y) * c.rho0;
         } else {
             if (!rigid_on) return;
-            s = ki_rho * c.rho0;
+            s = (-pj.w) * kernel_gradient_scale(c, r2) * ki_rho * c.rho0;
             if (c.has_dynamic_rigid && __ldg(d.is_dynamic + j)) {
-                float3 force = g * (s * c.inv_dt * (pi.w * c.rho0));
-                add_wrench(d, __ldg(d.object_id + j), force, f3(__ldg(d.pv + j)));
+                float3 force = R * (s * c.inv_dt * (pi.w * c.rho0));
+                add_wrench(d, __ldg(d.object_id + j), force, f3(pj));
             }
         }
-        dv.x = fmaf(-s, g.x, dv.x); dv.y = fmaf(-s, g.y, dv.y); dv.z = fmaf(-s, g.z, dv.z);
+        dv.x = fmaf(-s, R.x, dv.x); dv.y = fmaf(-s, R.y, dv.y); dv.z = fmaf(-s, R.z, dv.z);
     });
     float4 v = d.vm[i];
     v = make_float4(v.x + dv.x, v.y + dv.y, v.z + dv.z, v.w);
@@ -565,8 +515,7 @@ void set_smem_limit(K kernel, size_t bytes) {
 bool sph_lists_ready(SphHandle* h) {
     if (!h->lists_enabled) return false;
     if (!h->list_valid) {
-        if (h->d.pairg) LAUNCH_WIN(k_density<false, true, true>);
-        else LAUNCH_WIN(k_density<false, true, false>);
+        LAUNCH_WIN(k_density<false, true>);
         h->list_valid = true;
     }
     return true;
@@ -580,6 +529,7 @@ static void ensure_records(SphHandle* h, bool need_vel) {
         const int with_vel = !h->rec_vel_valid;
         k_sync_records<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d, with_vel);
         h->launches++;
+        if (with_vel) sph_ghost_dirty(h, GHOST_VEL);
     }
     h->rec_pos_valid = true;
     h->rec_vel_valid = true;
@@ -595,12 +545,8 @@ void sph_ghost_sync(SphHandle* h, int what) {
         h->rec_pos_valid = false;   // record copies of the ghosts' pv are refreshed by ensure_records
     }
     if (!rc && (need & GHOST_RHO)) rc = sph_slab_halo(h, h->d.rho, 4);
-    if (!rc && (need & GHOST_VEL)) {
-        rc = sph_slab_halo(h, h->d.vm, 16);
-        h->rec_vel_valid = false;   // recA.hi of the ghosts follows on the next record sync
-    }
+    if (!rc && (need & GHOST_VEL)) rc = sph_slab_halo(h, h->d.recA, 32);
     if (!rc && (need & GHOST_AUX)) rc = sph_slab_halo(h, h->d.recB, 32);
-    if (!rc && (need & GHOST_AUX2)) rc = sph_slab_halo(h, h->d.aux2, 8);
     if (rc && !h->sticky_rc) h->sticky_rc = rc;
     h->ghost_stale &= ~need;
 }
@@ -620,11 +566,10 @@ void sph_launch_density(SphHandle* h) {
     sph_ghost_sync(h, GHOST_PV);
     sph_ghost_dirty(h, GHOST_RHO);
     if (h->lists_enabled) {
-        if (h->d.pairg) LAUNCH_WIN(k_density<true, true, true>);
-        else LAUNCH_WIN(k_density<true, true, false>);
+        LAUNCH_WIN(k_density<true, true>);
         h->list_valid = true;
     } else {
-        LAUNCH_WIN(k_density<true, false, false>);
+        LAUNCH_WIN(k_density<true, false>);
     }
 }
 void sph_launch_pressure_accel(SphHandle* h) { sph_ghost_sync(h, GHOST_PV); ensure_records(h, false); prep_aux(h, AUX_PRESSURE); sph_ghost_sync(h, GHOST_AUX); LAUNCH_LIST(k_pressure_accel, false, ); }
@@ -636,32 +581,38 @@ void sph_launch_surface_tension(SphHandle* h) {
     h->ghost_stale &= ~GHOST_AUX;   // the ghosts' (rho, m) are local data: nothing to fetch
     LAUNCH_LIST(k_surface_tension, );
 }
-void sph_launch_viscosity(SphHandle* h, bool) { sph_ghost_sync(h, GHOST_PV | GHOST_RHO | GHOST_VEL); ensure_records(h, true); LAUNCH_LIST(k_viscosity, ); }
+void sph_launch_viscosity(SphHandle* h, bool) { sph_ghost_sync(h, GHOST_PV | GHOST_RHO); ensure_records(h, true); sph_ghost_sync(h, GHOST_VEL); LAUNCH_LIST(k_viscosity, ); }
 void sph_launch_dfsph_alpha(SphHandle* h) { sph_ghost_sync(h, GHOST_PV); LAUNCH_LIST(k_dfsph_alpha, ); }
 void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused) {
-    sph_ghost_sync(h, GHOST_PV | GHOST_VEL);
-    if (fused) sph_ghost_dirty(h, GHOST_AUX2);
+    sph_ghost_sync(h, GHOST_PV);
+    ensure_records(h, true);
+    sph_ghost_sync(h, GHOST_VEL);
+    if (fused) sph_ghost_dirty(h, GHOST_AUX);
     if (sph_lists_ready(h)) { if (fused) LAUNCH(k_dfsph_density_change<false, true, true>); else LAUNCH(k_dfsph_density_change<false, true, false>); }
     else { if (fused) LAUNCH(k_dfsph_density_change<false, false, true>); else LAUNCH(k_dfsph_density_change<false, false, false>); }
 }
 void sph_launch_dfsph_density_star(SphHandle* h, bool fused) {
-    sph_ghost_sync(h, GHOST_PV | GHOST_VEL);
-    if (fused) sph_ghost_dirty(h, GHOST_AUX2);
+    sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
+    ensure_records(h, true);
+    sph_ghost_sync(h, GHOST_VEL);
+    if (fused) sph_ghost_dirty(h, GHOST_AUX);
     if (sph_lists_ready(h)) { if (fused) LAUNCH(k_dfsph_density_change<true, true, true>); else LAUNCH(k_dfsph_density_change<true, true, false>); }
     else { if (fused) LAUNCH(k_dfsph_density_change<true, false, true>); else LAUNCH(k_dfsph_density_change<true, false, false>); }
 }
 // aux_ready: the fused density-change kernel has just written recB.hi = (kappa, kappa/rho, rho, m)
 void sph_launch_dfsph_correct_divergence(SphHandle* h, bool aux_ready) {
-    sph_ghost_sync(h, GHOST_PV);
-    if (!aux_ready) { LAUNCH(k_prep_aux2<true>); sph_ghost_dirty(h, GHOST_AUX2); }
-    sph_ghost_sync(h, GHOST_AUX2);
+    sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
+    ensure_records(h, false);
+    if (!aux_ready) prep_aux(h, AUX_KAPPA_V);
+    sph_ghost_sync(h, GHOST_AUX);
     LAUNCH_LIST(k_dfsph_correct, );
     sph_ghost_dirty(h, GHOST_VEL);
 }
 void sph_launch_dfsph_correct_density(SphHandle* h, bool aux_ready) {
-    sph_ghost_sync(h, GHOST_PV);
-    if (!aux_ready) { LAUNCH(k_prep_aux2<false>); sph_ghost_dirty(h, GHOST_AUX2); }
-    sph_ghost_sync(h, GHOST_AUX2);
+    sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
+    ensure_records(h, false);
+    if (!aux_ready) prep_aux(h, AUX_KAPPA);
+    sph_ghost_sync(h, GHOST_AUX);
     LAUNCH_LIST(k_dfsph_correct, );
     sph_ghost_dirty(h, GHOST_VEL);
 }
