@@ -51,15 +51,10 @@ def algo_bytes(kernel, n_total, n_pairs):
     neighbour list itself (4 B per accepted pair) for the kernel that writes it (k_density<.., true>)
     and for the kernels that stream it instead of re-deriving it from positions."""
     base = kernel.split("<")[0]
-    smem = base.endswith("_smem")      # shared-memory iteration kernels stream the 16-bit slot list
-    if smem:
-        base = base[:-5]
     if base not in ALGO_BYTES:
         return None
     b = ALGO_BYTES[base] * n_total
     args = kernel.replace(" ", "")
-    if smem:
-        return b + 2 * n_pairs
     if base == "k_density" and args.endswith(",true>"):
         b += 4 * n_pairs + 4 * n_total
     if base in LIST_CONSUMERS and args.endswith("true>") and not (base == "k_dfsph_density_change" and args.endswith(",false,true>")):

@@ -423,19 +423,13 @@ int sph_create(const SphParams* p, SphHandle** out) {
         const char* k = getenv("SPH_B200_KMAX");
         d.nbr_kmax = k ? atoi(k) : 96;
         if (d.nbr_kmax < 1) d.nbr_kmax = 1;
-        d.nbr_stride = (int)((n + SPH_BLOCK - 1) / SPH_BLOCK * SPH_BLOCK);   // whole chunks: list tiles are TMA-copied per chunk
+        d.nbr_stride = (int)((n + 31) / 32 * 32);
         if (h->lists_enabled) { ALLOC(d.nbr, (size_t)d.nbr_kmax * (size_t)d.nbr_stride); }
         ALLOC(d.nbr_count, n);
         ALLOC(d.chunk_desc, (n / SPH_BLOCK + 2) * 40);
         ALLOC(d.win_stats, 4);
         ALLOC(d.recA, n);
         ALLOC(d.recB, n);
-        ALLOC(d.aux4, n);
-        {   // shared-memory solver-iteration kernels (DFSPH): SPH_B200_SMEM_ITER=0 keeps the L1-gather versions
-            const char* e2 = getenv("SPH_B200_SMEM_ITER");
-            h->smem_iter = !(e2 && e2[0] == '0') && h->lists_enabled && p->method == SPH_METHOD_DFSPH;
-            if (h->smem_iter) { ALLOC(d.nbr16, (size_t)d.nbr_kmax * (size_t)d.nbr_stride); }
-        }
         const char* w = getenv("SPH_B200_WMAX");   // window slots per CTA (16 B x payload arrays each)
         h->wmax = w ? atoi(w) : 1536;
         if (h->wmax < 64) h->wmax = 64;

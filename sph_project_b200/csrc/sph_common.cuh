@@ -100,10 +100,6 @@ struct Dev {
     //                                              DFSPH correction, (p/rho^2, p) for the pressure force
     Rec* recA;
     Rec* recB;
-    // DFSPH solver iterations (shared-memory kernels): 16-bit window-slot twin of nbr, and
-    // aux4[j] = (kappa_j, kappa_j / rho_j, rho_j, m_j) as a plain float4 array that TMA can stage
-    unsigned short* nbr16;
-    float4* aux4;
 };
 
 // one 256-bit read-only gather of a neighbour record
@@ -223,7 +219,6 @@ struct SphHandle {
     int ghost_stale = 0;
     int sticky_rc = 0;           // first error raised inside a void launcher (NCCL), reported by the caller
     int wmax = 1536;             // shared-memory window budget (slots) of the sweep kernels
-    bool smem_iter = false;      // DFSPH iteration kernels read staged shared-memory tiles
     // per-kernel event timing (sph_profile_enable / sph_profile_read)
     cudaStream_t own_stream = nullptr;
     bool profiling = false;

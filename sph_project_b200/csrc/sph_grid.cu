@@ -205,7 +205,6 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_chunk_windows(Consts c, Dev d, in
     }
     desc[0] = total;
     desc[1] = ncp;
-    desc[3] = 0;   // max neighbour count of the chunk, filled by the list build
     atomicMax(d.win_stats + 0, total);
     if (total > wmax) atomicAdd(d.win_stats + 1, 1);
 }

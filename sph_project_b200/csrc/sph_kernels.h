@@ -34,7 +34,7 @@ __device__ __forceinline__ void block_reduce_add(double* dst, double v) {
 #endif
 
 // sph_slab.cu
-enum GhostField { GHOST_VEL = 1, GHOST_AUX = 2, GHOST_RHO = 4, GHOST_PV = 8, GHOST_AUX4 = 16 };
+enum GhostField { GHOST_VEL = 1, GHOST_AUX = 2, GHOST_RHO = 4, GHOST_PV = 8 };
 bool sph_is_slab(const SphHandle* h);
 int sph_slab_pre_sort(SphHandle* h);
 int sph_slab_post_scan(SphHandle* h);

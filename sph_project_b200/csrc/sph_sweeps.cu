@@ -122,14 +122,14 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_prep_aux(Consts c, Dev d) {
 }
 
 // refresh the record copies of pv / vm (host-side edits, kernels that do not write the records)
-__global__ void __launch_bounds__(SPH_BLOCK) k_sync_records(Consts c, Dev d, int with_vel, int all_rows) {
+__global__ void __launch_bounds__(SPH_BLOCK) k_sync_records(Consts c, Dev d, int with_vel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.N) return;
     const float4 p = d.pv[i];
     d.recA[i].lo = p;
     d.recB[i].lo = p;
-    // L1-gather mode: ghost velocities live in recA only (halo target), never re-derived from vm
-    if (with_vel && (all_rows || SPH_IS_ROW(c, i))) d.recA[i].hi = d.vm[i];
+    // ghost velocities live in recA only (refreshed by halos), never re-derived from the ghosts' vm
+    if (with_vel && SPH_IS_ROW(c, i)) d.recA[i].hi = d.vm[i];
 }
 
 // compute_rigid_particle_volume (base_solver.py:105-123); rigid rows, plain window walk in global
@@ -171,24 +171,17 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_density(Consts c, Dev d, int wmax
     int* col = d.nbr + i;
     const size_t stride = (size_t)d.nbr_stride;
     const int kmax = d.nbr_kmax;
-    unsigned short* col16 = d.nbr16 ? d.nbr16 + i : nullptr;   // window-slot twin of the list (DFSPH iteration kernels)
-    auto body = [&](int j, int w, float4 pj, float3, float r2) {
+    auto body = [&](int j, float4 pj, float3, float r2) {
         if (DENSITY) ret += fabsf(pj.w) * kernel_W_q(c, sqrtf(r2) * c.inv_h);
         if (BUILD) {
-            if (n < kmax) {
-                col[(size_t)n * stride] = j;
-                if (col16) col16[(size_t)n * stride] = (unsigned short)w;
-            }
+            if (n < kmax) col[(size_t)n * stride] = j;
             n++;
         }
     };
     if (win.staged) window_walk(c, d, win, i, pi, body);
-    else for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) { body(j, 0, pj, R, r2); });
+    else for_all_neighbors(c, d, i, pi, body);
     if (DENSITY) d.rho[i] = (pi.w * c.kW + ret) * c.rho0;
-    if (BUILD) {
-        d.nbr_count[i] = n;   // may exceed kmax: such rows re-derive their neighbours
-        if (col16) atomicMax(d.chunk_desc + (size_t)blockIdx.x * SPH_DESC_INTS + 3, min(n, kmax));
-    }
+    if (BUILD) d.nbr_count[i] = n;   // may exceed kmax: such rows re-derive their neighbours
 }
 
 // compute_pressure_acceleration (base_solver.py:135-187) and, with TEMP, PCISPH's
@@ -368,125 +361,6 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_correct(Consts c, Dev d) {
     d.recA[i].hi = v;
 }
 
-// ---- shared-memory versions of the two DFSPH solver-iteration kernels --------------------------
-// ~50 launches per pressurised step.  The L1-gather versions above sit at the L1 limit of about one
-// 32-byte sector per clock per SM (ncu: l1tex 80-91 % of peak); shared memory serves random 16-byte
-// reads about four times faster.  One CTA per chunk: TMA stages the chunk's pv window, the second
-// payload array (vm or aux4) and the chunk's tile of the 16-bit slot list; the loop then touches
-// shared memory only.  Chunks whose window exceeds the budget and rows that overflow the list take
-// the global path with the same arithmetic and order.
-
-// fallback: neighbours from the 32-bit list (or the window walk) with plain gathers of pv and b
-template <class Visit>
-__device__ __forceinline__ void pvb_neighbors(const Consts& c, const Dev& d, const float4* __restrict__ b, int i, float4 pi, Visit&& visit) {
-    const int n = d.nbr_count[i];
-    if (d.nbr && n <= d.nbr_kmax) {
-        const int* __restrict__ col = d.nbr + i;
-        const size_t stride = (size_t)d.nbr_stride;
-        for (int k = 0; k < n; k++) {
-            const int j = __ldg(col + (size_t)k * stride);
-            const float4 pj = __ldg(d.pv + j);
-            const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-            visit(pj, __ldg(b + j), R, dist2(R));
-        }
-        return;
-    }
-    for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) { visit(pj, __ldg(b + j), R, r2); });
-}
-
-template <class Visit>
-__device__ __forceinline__ void window2_neighbors(const Consts& c, const Dev& d, const Window2& win, const float4* b, int i, float4 pi,
-                                                  Visit&& visit) {
-    if (win.staged) {
-        const int n = d.nbr_count[i];
-        if (n <= d.nbr_kmax) {
-            window2_list(d, win, i, n, pi, visit);
-            return;
-        }
-    }
-    pvb_neighbors(c, d, b, i, pi, visit);
-}
-
-// aux4[i] = (kappa_i, kappa_i / rho_i, rho_i, m_i) for the unfused (task-by-task) path
-template <bool DIVERGENCE>
-__global__ void __launch_bounds__(SPH_BLOCK) k_prep_aux4(Consts c, Dev d) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.N) return;
-    const float k = DIVERGENCE ? d.kappa_v[i] : d.kappa[i];
-    const float rho = d.rho[i];
-    d.aux4[i] = make_float4(k, k / rho, rho, reinterpret_cast<const float*>(d.vm + i)[3]);
-}
-
-// compute_density_derivative / compute_density_star (DFSPH.py:65-126) (+ kappa + error when FUSED)
-template <bool STAR, bool FUSED>
-__global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change_smem(Consts c, Dev d, int wmax) {
-    __shared__ int s_desc[SPH_DESC_INTS];
-    __shared__ unsigned long long s_mbar;
-    const Window2 win = window_open2(d, d.vm, dyn_smem, wmax, s_desc, &s_mbar);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float err = 0.0f;
-    if (SPH_IS_ROW(c, i)) {
-        const float4 pi = d.pv[i];
-        if (pi.w > 0.0f) {
-            const float4 vi = d.vm[i];
-            float delta = 0.0f;
-            int nn = 0;
-            window2_neighbors(c, d, win, d.vm, i, pi, [&](float4 pj, float4 vj, float3 R, float r2) {
-                const float vr = dot3(make_float3(vi.x - vj.x, vi.y - vj.y, vi.z - vj.z), R);
-                delta = fmaf(fabsf(pj.w) * kernel_gradient_scale(c, r2), vr, delta);
-                nn++;
-            });
-            const float rho = d.rho[i];
-            float kap;
-            if (STAR) {
-                const float rs = fmaxf(rho / c.rho0 + c.dt * delta, 1.0f);
-                d.rho_star[i] = rs;
-                kap = (rs - 1.0f) * d.alpha[i] * c.inv_dt;
-                if (FUSED) { d.kappa[i] = kap; err = rs - 1.0f; }
-            } else {
-                float adv = fmaxf(delta, 0.0f);
-                if (nn < 20) adv = 0.0f;   // particle deficiency (DFSPH.py:93-95)
-                d.drho[i] = adv;
-                kap = adv * d.alpha[i];
-                if (FUSED) { d.kappa_v[i] = kap; err = c.rho0 * adv; }
-            }
-            if (FUSED) d.aux4[i] = make_float4(kap, kap / rho, rho, vi.w);
-        }
-    }
-    if (FUSED) block_reduce_add(d.red + RED_ERR, (double)err);
-}
-
-// correct_divergence_step / correct_density_error_step (DFSPH.py:161-202, 245-283)
-__global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_correct_smem(Consts c, Dev d, int wmax) {
-    __shared__ int s_desc[SPH_DESC_INTS];
-    __shared__ unsigned long long s_mbar;
-    const Window2 win = window_open2(d, d.aux4, dyn_smem, wmax, s_desc, &s_mbar);
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    SPH_ROW_OR_RETURN(c, i);
-    const float4 pi = d.pv[i];
-    if (!(pi.w > 0.0f)) return;
-    const float4 ai = d.aux4[i];
-    const float k_i = ai.x, ki_rho = ai.y;
-    const float thresh = 1e-5f * c.dt;   // m_eps * dt
-    const bool rigid_on = fabsf(k_i) > thresh;
-    float3 dv = make_float3(0.f, 0.f, 0.f);
-    window2_neighbors(c, d, win, d.aux4, i, pi, [&](float4 pj, float4 aj, float3 R, float r2) {
-        float s;
-        if (pj.w > 0.0f) {
-            if (!(fabsf(k_i + aj.x) > thresh)) return;
-            s = pj.w * kernel_gradient_scale(c, r2) * (ki_rho + aj.y) * c.rho0;
-        } else {
-            if (!rigid_on) return;
-            s = (-pj.w) * kernel_gradient_scale(c, r2) * ki_rho * c.rho0;
-        }
-        dv.x = fmaf(-s, R.x, dv.x); dv.y = fmaf(-s, R.y, dv.y); dv.z = fmaf(-s, R.z, dv.z);
-    });
-    float4 v = d.vm[i];
-    v = make_float4(v.x + dv.x, v.y + dv.y, v.z + dv.z, v.w);
-    d.vm[i] = v;
-    d.recA[i].hi = v;
-}
-
 // PCISPH compute_density_star (PCISPH.py:32-62): predicted positions, no self term, neighbour
 // set from the current positions.  Accumulates sum max(0, rho*/rho0 - 1) into red[RED_ERR].
 template <bool LIST>
@@ -631,18 +505,6 @@ void set_smem_limit(K kernel, size_t bytes) {
         }                                                                     \
     } while (0)
 
-// solver-iteration kernel: pv window + one payload window + the chunk's 16-bit list tile
-#define LAUNCH_WIN2(...)                                                      \
-    do {                                                                      \
-        if (h->c.N > 0) {                                                     \
-            SphProf _prof(h, #__VA_ARGS__);                                   \
-            const size_t smem_ = (size_t)h->wmax * 32 + SPH_LIST_TILE_ROWS * SPH_BLOCK * 2; \
-            set_smem_limit(__VA_ARGS__, smem_);                               \
-            __VA_ARGS__<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, smem_, h->stream>>>(h->c, h->d, h->wmax); \
-            h->launches++;                                                    \
-        }                                                                     \
-    } while (0)
-
 #define LAUNCH_LIST(kernel, ...)                                              \
     do {                                                                      \
         if (sph_lists_ready(h)) LAUNCH(kernel<__VA_ARGS__ true>);             \
@@ -665,9 +527,9 @@ static void ensure_records(SphHandle* h, bool need_vel) {
     if (h->c.N > 0) {
         SphProf _prof(h, "k_sync_records");
         const int with_vel = !h->rec_vel_valid;
-        k_sync_records<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d, with_vel, h->smem_iter ? 1 : 0);
+        k_sync_records<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d, with_vel);
         h->launches++;
-        if (with_vel && !h->smem_iter) sph_ghost_dirty(h, GHOST_VEL);
+        if (with_vel) sph_ghost_dirty(h, GHOST_VEL);
     }
     h->rec_pos_valid = true;
     h->rec_vel_valid = true;
@@ -683,16 +545,8 @@ void sph_ghost_sync(SphHandle* h, int what) {
         h->rec_pos_valid = false;   // record copies of the ghosts' pv are refreshed by ensure_records
     }
     if (!rc && (need & GHOST_RHO)) rc = sph_slab_halo(h, h->d.rho, 4);
-    if (!rc && (need & GHOST_VEL)) {
-        if (h->smem_iter) {            // the shared-memory kernels stage vm itself
-            rc = sph_slab_halo(h, h->d.vm, 16);
-            h->rec_vel_valid = false;  // recA.hi of the ghosts follows at the next record sync
-        } else {
-            rc = sph_slab_halo(h, h->d.recA, 32);
-        }
-    }
+    if (!rc && (need & GHOST_VEL)) rc = sph_slab_halo(h, h->d.recA, 32);
     if (!rc && (need & GHOST_AUX)) rc = sph_slab_halo(h, h->d.recB, 32);
-    if (!rc && (need & GHOST_AUX4)) rc = sph_slab_halo(h, h->d.aux4, 16);
     if (rc && !h->sticky_rc) h->sticky_rc = rc;
     h->ghost_stale &= ~need;
 }
@@ -727,21 +581,9 @@ void sph_launch_surface_tension(SphHandle* h) {
     h->ghost_stale &= ~GHOST_AUX;   // the ghosts' (rho, m) are local data: nothing to fetch
     LAUNCH_LIST(k_surface_tension, );
 }
-void sph_launch_viscosity(SphHandle* h, bool) {
-    sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
-    if (h->smem_iter) sph_ghost_sync(h, GHOST_VEL);   // lands in vm; the record sync below mirrors it
-    ensure_records(h, true);
-    sph_ghost_sync(h, GHOST_VEL);                      // L1-gather mode: lands in recA directly
-    LAUNCH_LIST(k_viscosity, );
-}
+void sph_launch_viscosity(SphHandle* h, bool) { sph_ghost_sync(h, GHOST_PV | GHOST_RHO); ensure_records(h, true); sph_ghost_sync(h, GHOST_VEL); LAUNCH_LIST(k_viscosity, ); }
 void sph_launch_dfsph_alpha(SphHandle* h) { sph_ghost_sync(h, GHOST_PV); LAUNCH_LIST(k_dfsph_alpha, ); }
 void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused) {
-    if (h->smem_iter && sph_lists_ready(h)) {
-        sph_ghost_sync(h, GHOST_PV | GHOST_VEL);
-        if (fused) { sph_ghost_dirty(h, GHOST_AUX4); LAUNCH_WIN2(k_dfsph_density_change_smem<false, true>); }
-        else LAUNCH_WIN2(k_dfsph_density_change_smem<false, false>);
-        return;
-    }
     sph_ghost_sync(h, GHOST_PV);
     ensure_records(h, true);
     sph_ghost_sync(h, GHOST_VEL);
@@ -750,12 +592,6 @@ void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused) {
     else { if (fused) LAUNCH(k_dfsph_density_change<false, false, true>); else LAUNCH(k_dfsph_density_change<false, false, false>); }
 }
 void sph_launch_dfsph_density_star(SphHandle* h, bool fused) {
-    if (h->smem_iter && sph_lists_ready(h)) {
-        sph_ghost_sync(h, GHOST_PV | GHOST_RHO | GHOST_VEL);
-        if (fused) { sph_ghost_dirty(h, GHOST_AUX4); LAUNCH_WIN2(k_dfsph_density_change_smem<true, true>); }
-        else LAUNCH_WIN2(k_dfsph_density_change_smem<true, false>);
-        return;
-    }
     sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
     ensure_records(h, true);
     sph_ghost_sync(h, GHOST_VEL);
@@ -764,22 +600,7 @@ void sph_launch_dfsph_density_star(SphHandle* h, bool fused) {
     else { if (fused) LAUNCH(k_dfsph_density_change<true, false, true>); else LAUNCH(k_dfsph_density_change<true, false, false>); }
 }
 // aux_ready: the fused density-change kernel has just written recB.hi = (kappa, kappa/rho, rho, m)
-// shared-memory variant of both correction steps; aux4 = (kappa, kappa/rho, rho, m)
-static bool correct_smem(SphHandle* h, bool aux_ready, bool divergence) {
-    if (!(h->smem_iter && !h->c.has_dynamic_rigid && sph_lists_ready(h))) return false;
-    sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
-    if (!aux_ready) {
-        if (divergence) LAUNCH(k_prep_aux4<true>); else LAUNCH(k_prep_aux4<false>);
-        sph_ghost_dirty(h, GHOST_AUX4);
-    }
-    sph_ghost_sync(h, GHOST_AUX4);
-    LAUNCH_WIN2(k_dfsph_correct_smem);
-    sph_ghost_dirty(h, GHOST_VEL);
-    return true;
-}
-
 void sph_launch_dfsph_correct_divergence(SphHandle* h, bool aux_ready) {
-    if (correct_smem(h, aux_ready, true)) return;
     sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
     ensure_records(h, false);
     if (!aux_ready) prep_aux(h, AUX_KAPPA_V);
@@ -788,7 +609,6 @@ void sph_launch_dfsph_correct_divergence(SphHandle* h, bool aux_ready) {
     sph_ghost_dirty(h, GHOST_VEL);
 }
 void sph_launch_dfsph_correct_density(SphHandle* h, bool aux_ready) {
-    if (correct_smem(h, aux_ready, false)) return;
     sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
     ensure_records(h, false);
     if (!aux_ready) prep_aux(h, AUX_KAPPA);

@@ -89,84 +89,8 @@ __device__ __forceinline__ Window window_open(const Dev& d, float4* smem, int wm
     return w;
 }
 
-// Solver-iteration kernels: stage TWO payload arrays (pv + one float4 array) and the chunk's tile of
-// the 16-bit slot list (rows k < n_rows of nbr16[k][chunk], 256 B each) so that the inner loop reads
-// shared memory only.
-#define SPH_LIST_TILE_ROWS 64
-struct Window2 {
-    const float4* s_pv;
-    const float4* s_b;
-    const unsigned short* s_list;   // [SPH_LIST_TILE_ROWS][SPH_BLOCK]
-    int list_rows;
-    bool staged;
-};
-__device__ __forceinline__ Window2 window_open2(const Dev& d, const float4* payload_b, float4* smem, int wmax, int* s_desc,
-                                                unsigned long long* s_mbar) {
-    const int tid = threadIdx.x;
-    if (tid < SPH_DESC_INTS) s_desc[tid] = d.chunk_desc[(size_t)blockIdx.x * SPH_DESC_INTS + tid];
-    if (tid == 0) {
-        mbar_init(s_mbar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    Window2 w;
-    w.s_pv = smem;
-    w.s_b = smem + wmax;
-    unsigned short* s_list = reinterpret_cast<unsigned short*>(smem + 2 * (size_t)wmax);
-    w.s_list = s_list;
-    const int total = s_desc[0];
-    w.list_rows = min(s_desc[3], SPH_LIST_TILE_ROWS);
-    w.staged = s_desc[2] > 0 && total <= wmax && d.nbr16 != nullptr;
-    if (w.staged) {
-        if (tid == 0) {
-            mbar_arrive_expect_tx(s_mbar, (unsigned)total * 32u + (unsigned)w.list_rows * (SPH_BLOCK * 2u));
-            const int ncp = s_desc[1];
-            int s = 0;
-            for (int c = 0; c < ncp; c++) {
-                const int g = s_desc[22 + c], n = s_desc[31 + c];
-                tma_bulk_load(smem + s, d.pv + g, (unsigned)n * 16u, s_mbar);
-                tma_bulk_load(smem + wmax + s, payload_b + g, (unsigned)n * 16u, s_mbar);
-                s += n;
-            }
-            const unsigned short* src = d.nbr16 + (size_t)blockIdx.x * SPH_BLOCK;
-            for (int k = 0; k < w.list_rows; k++)
-                tma_bulk_load(s_list + k * SPH_BLOCK, src + (size_t)k * d.nbr_stride, SPH_BLOCK * 2u, s_mbar);
-        }
-        mbar_wait(s_mbar, 0);
-    }
-    return w;
-}
-
-// neighbours of the thread's particle from the staged tile: visit(pj, bj, R, r2)
-template <class Visit>
-__device__ __forceinline__ void window2_list(const Dev& d, const Window2& win, int i, int n, float4 pi, Visit&& visit) {
-    const unsigned short* __restrict__ s_col = win.s_list + threadIdx.x;
-    const unsigned short* __restrict__ g_col = d.nbr16 + i;
-    const size_t stride = (size_t)d.nbr_stride;
-    const int rows = win.list_rows;
-    int k = 0;
-    const int n_tile = min(n, rows);
-    for (; k + 4 <= n_tile; k += 4) {
-        const int w0 = s_col[k * SPH_BLOCK], w1 = s_col[(k + 1) * SPH_BLOCK], w2 = s_col[(k + 2) * SPH_BLOCK], w3 = s_col[(k + 3) * SPH_BLOCK];
-        const float4 p0 = win.s_pv[w0], p1 = win.s_pv[w1], p2 = win.s_pv[w2], p3 = win.s_pv[w3];
-        const float4 b0 = win.s_b[w0], b1 = win.s_b[w1], b2 = win.s_b[w2], b3 = win.s_b[w3];
-        float3 R;
-        R = make_float3(pi.x - p0.x, pi.y - p0.y, pi.z - p0.z); visit(p0, b0, R, dist2(R));
-        R = make_float3(pi.x - p1.x, pi.y - p1.y, pi.z - p1.z); visit(p1, b1, R, dist2(R));
-        R = make_float3(pi.x - p2.x, pi.y - p2.y, pi.z - p2.z); visit(p2, b2, R, dist2(R));
-        R = make_float3(pi.x - p3.x, pi.y - p3.y, pi.z - p3.z); visit(p3, b3, R, dist2(R));
-    }
-    for (; k < n; k++) {   // tail, and rows beyond the staged tile
-        const int w = k < rows ? (int)s_col[k * SPH_BLOCK] : (int)__ldg(g_col + (size_t)k * stride);
-        const float4 pj = win.s_pv[w], bj = win.s_b[w];
-        const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-        visit(pj, bj, R, dist2(R));
-    }
-}
-
 // Walk the 27-cell window of particle i with candidates read from the staged window.
-// visit(j, w, pj, R, r2) for every accepted neighbour j (sorted index; w = its window slot), same
-// order as for_all_neighbors.
+// visit(j, pj, R, r2) for every accepted neighbour j (sorted index), same order as for_all_neighbors.
 template <class Visit>
 __device__ __forceinline__ void window_walk(const Consts& c, const Dev& d, const Window& win, int i, float4 pi, Visit&& visit) {
     const int3 g = cell_of(c, pi.x, pi.y, pi.z);
@@ -190,7 +114,7 @@ __device__ __forceinline__ void window_walk(const Consts& c, const Dev& d, const
                 const float4 pj = s_pv[w];
                 const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
                 const float r2 = dist2(R);
-                if (r2 < c.h2_thresh && j != i) visit(j, w, pj, R, r2);
+                if (r2 < c.h2_thresh && j != i) visit(j, pj, R, r2);
             }
         }
     }
