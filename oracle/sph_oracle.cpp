@@ -16,7 +16,7 @@
 // they meet an f32 operand.  Build with -ffp-contract=off so the only fused operation is the
 // explicit fmaf in dist2() (the canonical squared distance shared with the CUDA path so both
 // produce bit-identical neighbour sets).  Reductions that the reference does with f32 atomics in
-// nondeterministic order are accumulated in f64 in index order and rounded once.
+// nondeterministic order are accumulated in f64 (OpenMP partial sums) and rounded once.
 //
 // Sort order: stable counting sort on the reference's z-fastest flatten (base_container.py:472-481);
 // upstream's in-cell order is nondeterministic (atomic_sub from many threads, :510-515) but equals
@@ -286,6 +286,7 @@ void compute_density(SphHandle& s) {
 
 // base_solver.py:135-187
 void compute_pressure_acceleration(SphHandle& s) {
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.cap; i++) s.a[i] = {0, 0, 0};  // .fill(0.0) over the whole field
 #pragma omp parallel for schedule(dynamic, 256)
     for (int i = 0; i < s.N; i++) {
@@ -317,6 +318,7 @@ void compute_pressure_acceleration(SphHandle& s) {
 
 // base_solver.py:202-207
 void compute_gravity_acceleration(SphHandle& s) {
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.a[i] = s.g;
 }
@@ -425,6 +427,7 @@ void cg_prepare1(SphHandle& s) {  // :281-315
 }
 
 void cg_prepare2(SphHandle& s) {  // :317-323
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) {
             s.cg_r[i] = mv(s.cg_dinv[i], s.cg_b[i]) - s.cg_Ap[i];
@@ -461,6 +464,7 @@ void cg_compute_alpha(SphHandle& s) {  // :393-406
 }
 
 void cg_update_x(SphHandle& s) {  // :408-412
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.cg_x[i] += s.cg_alpha * s.cg_p[i];
 }
@@ -480,21 +484,25 @@ void cg_update_r_and_beta(SphHandle& s) {  // :414-431
 }
 
 void cg_update_p(SphHandle& s) {  // :433-437
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.cg_p[i] = s.cg_r[i] + s.cg_beta * s.cg_p[i];
 }
 
 void cg_prepare_guess(SphHandle& s) {  // :439-443
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.cg_x[i] -= s.v_orig[i];
 }
 
 void viscosity_update_velocity(SphHandle& s) {  // :463-467
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.v[i] = s.cg_x[i];
 }
 
 void copy_back_original_velocity(SphHandle& s) {  // :469-473
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.v[i] = s.v_orig[i];
 }
@@ -542,6 +550,7 @@ int compute_non_pressure_acceleration(SphHandle& s, int* cg_it) {
 
 // base_solver.py:574-605 (+ simulate_collisions :544-549)
 void enforce_domain_boundary_3D(SphHandle& s, int particle_type) {
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++) {
         if (!(s.material[i] == particle_type && s.is_dynamic[i])) continue;
         V3 pos = s.x[i];
@@ -563,6 +572,7 @@ void enforce_domain_boundary_3D(SphHandle& s, int particle_type) {
 
 // base_solver.py:615-629
 void renew_rigid_particle_state(SphHandle& s) {
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++) {
         if (!(s.material[i] == SPH_MATERIAL_RIGID && s.is_dynamic[i])) continue;
         int obj = s.object_id[i];
@@ -577,12 +587,14 @@ void renew_rigid_particle_state(SphHandle& s) {
 
 // base_solver.py:642-649
 void update_fluid_velocity(SphHandle& s) {
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.v[i] += s.dt * s.a[i];
 }
 
 // base_solver.py:651-666
 void update_fluid_position(SphHandle& s) {
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++) {
         if (s.material[i] == SPH_MATERIAL_FLUID) {
             s.x[i] += s.dt * s.v[i];
@@ -599,6 +611,7 @@ void update_fluid_position(SphHandle& s) {
 
 // base_solver.py:669-677
 void prepare_emitter(SphHandle& s) {
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID && s.x[i].y > s.g_upper) s.material[i] = SPH_MATERIAL_RIGID;
 }
@@ -606,6 +619,7 @@ void prepare_emitter(SphHandle& s) {
 // ---- WCSPH.py:16-24 ----
 void wcsph_compute_pressure(SphHandle& s) {
     const float gamma = 7.0f, stiffness = 50000.0f;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) {
             float rho_i = std::max(s.rho[i], s.rho0);
@@ -663,12 +677,14 @@ void dfsph_compute_density_star(SphHandle& s) {  // :104-126
 }
 
 void dfsph_compute_kappa_v(SphHandle& s) {  // :132-137
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.kappa_v[i] = s.drho[i] * s.alpha[i];
 }
 
 void dfsph_compute_kappa(SphHandle& s) {  // :217-223
     float dt_inv = 1 / s.dt;
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.kappa[i] = (s.rho_star[i] - 1.0f) * s.alpha[i] * dt_inv;
 }
@@ -720,6 +736,7 @@ void dfsph_correct_step(SphHandle& s, const std::vector<float>& kappa, bool accu
 
 float dfsph_compute_density_derivative_error(SphHandle& s) {  // :205-211
     double e = 0;
+#pragma omp parallel for schedule(static) reduction(+ : e)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) e += s.rho0 * s.drho[i];
     return (float)e / (float)s.N;
@@ -727,6 +744,7 @@ float dfsph_compute_density_derivative_error(SphHandle& s) {  // :205-211
 
 float dfsph_compute_density_error(SphHandle& s) {  // :285-294
     double e = 0;
+#pragma omp parallel for schedule(static) reduction(+ : e)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) e += s.rho_star[i] - 1.0f;
     return (float)e / (float)s.N;
@@ -771,10 +789,12 @@ void dfsph_correct_density_error(SphHandle& s, int* iters, float* err) {  // :22
 
 // ---- PCISPH.py ----
 void pcisph_compute_predicted_velocity(SphHandle& s) {  // :18-22
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.v_pred[i] = s.v[i] + s.dt * (s.a[i] + s.a_p[i]);
 }
 void pcisph_compute_predicted_position(SphHandle& s) {  // :25-29
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) s.x_pred[i] = s.x[i] + s.dt * s.v_pred[i];
 }
@@ -799,6 +819,7 @@ void pcisph_compute_density_star(SphHandle& s) {  // :32-62 (no self term; N(i) 
     s.density_error = s.Nfluid > 0 ? (float)e / (float)s.Nfluid : 0.f;
 }
 void pcisph_update_pressure(SphHandle& s) {  // :65-71
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < s.N; i++)
         if (s.material[i] == SPH_MATERIAL_FLUID) {
             s.p[i] += s.pcisph_k * (s.rho0 - s.rho_star[i]);

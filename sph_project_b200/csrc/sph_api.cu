@@ -322,7 +322,13 @@ int step_once(SphHandle* h, SphStepStats* st) {
         default:
             return fail(h, SPH_E_UNSUPPORTED, "unknown simulation method");
     }
-    sph_launch_rigid_volume(h);   // BaseSolver.step tail (base_solver.py:696)
+    // BaseSolver.step tail (base_solver.py:696).  Akinci volumes depend only on same-object rigid
+    // neighbours: for static boundaries they are bit-identical every step (stable sort keeps the
+    // rigid particles' relative order), so the sweep runs again only when something could change them.
+    if (!h->rigid_volume_clean) {
+        sph_launch_rigid_volume(h);
+        h->rigid_volume_clean = !h->c.has_dynamic_rigid;
+    }
     return last_launch(h);
 }
 
@@ -507,6 +513,7 @@ int sph_add_particles(SphHandle* h, int32_t object_id, int32_t n, const float* x
     h->sorted_valid = false;
     h->list_valid = false;
     h->rec_pos_valid = h->rec_vel_valid = false;
+    h->rigid_volume_clean = false;
     h->dyn_rigid_dirty = true;
     return SPH_OK;
 }
@@ -553,6 +560,7 @@ int sph_set_field(SphHandle* h, int32_t field, const void* src, size_t bytes) {
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (field == SPH_F_POSITION) h->sorted_valid = false;
     if (field == SPH_F_POSITION || field == SPH_F_MATERIAL) h->list_valid = false;
+    h->rigid_volume_clean = false;   // any host edit may touch what the boundary volumes depend on
     if (field == SPH_F_POSITION || field == SPH_F_MATERIAL || field == SPH_F_REST_VOLUME) h->rec_pos_valid = false;
     if (field == SPH_F_VELOCITY || field == SPH_F_MASS) h->rec_vel_valid = false;
     if (field == SPH_F_MATERIAL || field == SPH_F_IS_DYNAMIC) h->dyn_rigid_dirty = true;
@@ -573,6 +581,7 @@ int sph_fill_field(SphHandle* h, int32_t field, double value) {
     if (comps < 0) return fail(h, comps, "field not available for this solver");
     if (field == SPH_F_MATERIAL || field == SPH_F_IS_DYNAMIC) h->dyn_rigid_dirty = true;
     if (field == SPH_F_POSITION || field == SPH_F_MATERIAL) h->list_valid = false;
+    h->rigid_volume_clean = false;   // any host edit may touch what the boundary volumes depend on
     if (field == SPH_F_POSITION || field == SPH_F_MATERIAL || field == SPH_F_REST_VOLUME) h->rec_pos_valid = false;
     if (field == SPH_F_VELOCITY || field == SPH_F_MASS) h->rec_vel_valid = false;
     return last_launch(h);
@@ -642,7 +651,7 @@ int sph_set_scalar(SphHandle* h, int32_t s, double v) {
         case SPH_S_DT: h->P.dt = v; refresh_consts(h); break;
         case SPH_S_PARTICLE_NUM:
             if (v < 0 || v > h->c.cap) return fail(h, SPH_E_CAPACITY, "particle_num out of range");
-            h->c.N = (int)v; h->sorted_valid = false; h->list_valid = false; h->rec_pos_valid = h->rec_vel_valid = false; break;
+            h->c.N = (int)v; h->rigid_volume_clean = false; h->sorted_valid = false; h->list_valid = false; h->rec_pos_valid = h->rec_vel_valid = false; break;
         case SPH_S_FLUID_PARTICLE_NUM: h->Nfluid = (int)v; break;
         case SPH_S_PCISPH_K: h->c.pcisph_k = (float)v; break;
         case SPH_S_DENSITY_ERROR: h->density_error = (float)v; break;
@@ -801,8 +810,8 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
         case SPH_T_RENEW_RIGID_PARTICLE_STATE: sph_launch_renew_rigid(h); break;
         case SPH_T_UPDATE_FLUID_VELOCITY: sph_launch_update_velocity(h); break;
         case SPH_T_UPDATE_FLUID_POSITION: sph_launch_update_position(h); break;
-        case SPH_T_PREPARE_EMITTER: sph_launch_prepare_emitter(h); h->dyn_rigid_dirty = true; break;
-        case SPH_T_INIT_OBJECT_ID: sph_fill_i32(h, h->d.object_id, (size_t)h->c.cap, -1); break;
+        case SPH_T_PREPARE_EMITTER: sph_launch_prepare_emitter(h); h->dyn_rigid_dirty = true; h->rigid_volume_clean = false; break;
+        case SPH_T_INIT_OBJECT_ID: sph_fill_i32(h, h->d.object_id, (size_t)h->c.cap, -1); h->rigid_volume_clean = false; break;
         case SPH_T_INIT_ACCELERATION: sph_fill_f32(h, (float*)h->d.acc, (size_t)h->c.cap * 4, 0.0f); break;
         case SPH_T_INIT_RIGID_BODY_FORCE_AND_TORQUE: return sph_zero_rigid_wrench(h);
         case SPH_T_CG_PREPARE1: sph_launch_cg_prepare1_pre(h); sph_launch_cg_prepare1(h); break;

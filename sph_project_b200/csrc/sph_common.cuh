@@ -211,6 +211,7 @@ struct SphHandle {
     bool dyn_rigid_dirty = true;
     bool lists_enabled = true;   // SPH_B200_NO_LISTS=1 forces window walks (A/B testing)
     bool list_valid = false;     // nbr lists match the current positions and order
+    bool rigid_volume_clean = false;   // static boundary volumes are current (nothing added / edited since)
     bool rec_pos_valid = false;  // recA.lo / recB.lo mirror pv
     bool rec_vel_valid = false;  // recA.hi mirrors vm
     // Z-slab state (sph_slab.cu); ghost_stale = fields whose ghost copies lag their owners
