@@ -99,6 +99,11 @@ def oracle_library():
     """CPU oracle = the `reference` / cpu_baseline arm; never on the product path."""
     import ctypes
     from sph_project_b200 import _native
+    # pin the OpenMP team before libgomp starts: unpinned 128-thread teams on a 2-socket host wander
+    # between sockets and run the same sweep up to 3x slower from one process to the next
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_DYNAMIC", "false")
     path = os.path.join(ROOT, "oracle", "_build", "libsph_oracle.so")
     if not os.path.exists(path):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=sys.stderr)
@@ -410,6 +415,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # OpenMP placement of the CPU arms, fixed before any library starts an OpenMP runtime
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    os.environ.setdefault("OMP_PLACES", "cores")
+    os.environ.setdefault("OMP_DYNAMIC", "false")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
