@@ -99,11 +99,6 @@ def oracle_library():
     """CPU oracle = the `reference` / cpu_baseline arm; never on the product path."""
     import ctypes
     from sph_project_b200 import _native
-    # pin the OpenMP team before libgomp starts: unpinned 128-thread teams on a 2-socket host wander
-    # between sockets and run the same sweep up to 3x slower from one process to the next
-    os.environ.setdefault("OMP_PROC_BIND", "spread")
-    os.environ.setdefault("OMP_PLACES", "cores")
-    os.environ.setdefault("OMP_DYNAMIC", "false")
     path = os.path.join(ROOT, "oracle", "_build", "libsph_oracle.so")
     if not os.path.exists(path):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=sys.stderr)
@@ -415,10 +410,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    # OpenMP placement of the CPU arms, fixed before any library starts an OpenMP runtime
-    os.environ.setdefault("OMP_PROC_BIND", "spread")
-    os.environ.setdefault("OMP_PLACES", "cores")
-    os.environ.setdefault("OMP_DYNAMIC", "false")
+    # OpenMP placement of the CPU arms (the oracle), fixed before any library starts an OpenMP runtime.
+    # Single-process runs only: under torchrun every rank would bind its threads to the same first
+    # cores (measured: an 8-rank run with this set was ~70x slower, all host threads on one core).
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 or args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            os.environ.setdefault("OMP_PROC_BIND", "spread")
+            os.environ.setdefault("OMP_PLACES", "cores")
+            os.environ.setdefault("OMP_DYNAMIC", "false")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
