@@ -268,7 +268,7 @@ def run_gpu(args, rank, world, local_rank):
     rho_lower = lower_half_density(container)
     eng.step(args.warmup)
 
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(local_rank) if rank == 0 else None   # one nvidia-smi poller, not one per rank
     time.sleep(0.3)
     # ---- timed region: exactly K steps, device-resident state ----
     barrier()
@@ -276,13 +276,15 @@ def run_gpu(args, rank, world, local_rank):
     profiler_range = os.environ.get("SPH_BENCH_CUDA_PROFILER") == "1"   # ncu --profile-from-start off
     if profiler_range:
         torch.cuda.profiler.start()
-    clocks.mark()
+    if clocks:
+        clocks.mark()
     with torch.cuda.stream(stream):
         ev0.record(stream)
         stats = eng.step(args.steps)
         ev1.record(stream)
     barrier()
-    clocks.mark()
+    if clocks:
+        clocks.mark()
     if profiler_range:
         torch.cuda.profiler.stop()
     ms = ev0.elapsed_time(ev1)
@@ -291,7 +293,7 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = n_fluid * args.steps / (ms * 1e-3)
-    clock_info = clocks.stop()
+    clock_info = clocks.stop() if clocks else None
 
     # ---- roofline pass: per-launch events on the same stream ----
     eng.profile_enable(True)
