@@ -161,6 +161,16 @@ class BaseSolver:
 
     def renew_rigid_particle_state(self):
         self._renew_rigid_particle_state()
+        if self.cfg.get_cfg("exportObj"):   # keep the export meshes in step (base_solver.py:634-640)
+            c = self.container
+            for obj_i in range(c.object_num[None]):
+                if c.rigid_body_is_dynamic[obj_i] and c.object_materials[obj_i] == c.material_rigid:
+                    body = c.object_collection.get(obj_i)
+                    if not isinstance(body, dict) or "mesh" not in body:
+                        continue
+                    rot = np.asarray(c.rigid_body_rotations[obj_i], dtype=np.float64)
+                    com = np.asarray(c.rigid_body_centers_of_mass[obj_i], dtype=np.float64)
+                    body["mesh"].vertices = (rot @ (body["restPosition"] - body["restCenterOfMass"]).T).T + com
 
     def update_fluid_velocity(self):
         self._run(T.UPDATE_FLUID_VELOCITY)

@@ -11,3 +11,4 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "slow: takes more than a few seconds on CPU")
+    config.addinivalue_line("markers", "gpu_next: GPU tests written after the round's GPU budget was spent; not yet run on hardware")
