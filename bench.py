@@ -15,7 +15,10 @@ One JSON line on stdout (rank 0).  `value` counts FLUID particle-steps/s, whole 
   e2e          the same metric through host buffers: per step upload x, v from pinned memory,
                sph_step(1), download x, v
   cpu_baseline the CPU oracle (a restatement of the reference's algorithm; Taichi is not
-               installable here) on a bounded half-scale sample, all host cores
+               installable here) on the same workload for about 12 s, all host cores, early window
+
+N > 1 (torchrun, one rank per GPU): weak scaling — domain and fluid block grow along z by one
+1,231,200-particle slab per GPU, Z-slabs over NCCL inside the library (sph_project_b200/csrc/sph_slab.cu).
 
 `--impl reference` times that CPU restatement on the full workload instead (early window: it cannot
 afford the 1000-step pre-roll; its early-window rate is an upper bound of its pressurised rate).
