@@ -42,7 +42,7 @@ void rows_all(SphHandle* h) {
     if (!h->slab) {
         h->c.row_begin = 0;
         h->c.row_end = h->c.N;
-    } else if (!h->sorted_valid) {
+    } else if (!h->rows_from_sort) {
         h->c.row_begin = 0;          // before the first exchange every local particle is owned
         h->c.row_end = h->c.N;
     }

@@ -218,6 +218,7 @@ struct SphHandle {
     struct SlabState* slab = nullptr;
     long long n_global = 0;
     int ghost_stale = 0;
+    bool rows_from_sort = false; // owned range was set by a slab sort (host edits must not widen it to the ghosts)
     int sticky_rc = 0;           // first error raised inside a void launcher (NCCL), reported by the caller
     int wmax = 1536;             // shared-memory window budget (slots) of the sweep kernels
     // per-kernel event timing (sph_profile_enable / sph_profile_read)

@@ -268,6 +268,7 @@ int sph_slab_post_scan(SphHandle* h) {
     c.N = s->h_ints[14];             // dead particles sit in the trash cell beyond the live ones
     c.row_begin = s->own_begin;
     c.row_end = s->own_end;
+    h->rows_from_sort = true;
     return SPH_OK;
 }
 
