@@ -415,14 +415,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    # OpenMP placement of the CPU arms (the oracle), fixed before any library starts an OpenMP runtime.
-    # Single-process runs only: under torchrun every rank would bind its threads to the same first
-    # cores (measured: an 8-rank run with this set was ~70x slower, all host threads on one core).
-    if int(os.environ.get("WORLD_SIZE", "1")) == 1 or args.impl == "reference":
-        if int(os.environ.get("RANK", "0")) == 0:
-            os.environ.setdefault("OMP_PROC_BIND", "spread")
-            os.environ.setdefault("OMP_PLACES", "cores")
-            os.environ.setdefault("OMP_DYNAMIC", "false")
+    # OpenMP placement for the reference (CPU) arm only, fixed before the OpenMP runtime starts: the
+    # unpinned 128-thread team of that arm ran 3x slower than the same sweeps inside the GPU arm's
+    # cpu_baseline leg.  Never for the GPU arm: exported to all ranks of an 8-rank run it bound every
+    # rank's host threads to the same cores (~70x slower, profiles/r01_bench_8gpu_INVALID_*).
+    if args.impl == "reference" and int(os.environ.get("RANK", "0")) == 0:
+        os.environ.setdefault("OMP_PROC_BIND", "spread")
+        os.environ.setdefault("OMP_PLACES", "cores")
+        os.environ.setdefault("OMP_DYNAMIC", "false")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
