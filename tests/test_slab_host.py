@@ -88,3 +88,44 @@ def test_gloo_world_size_2(tmp_path):
            "--master-port", "29517", str(script)]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert out.returncode == 0 and out.stdout.count("WORKER_OK") == 2, out.stdout[-1500:] + out.stderr[-3000:]
+
+
+def test_halo_ranges_are_contiguous_and_aligned():
+    """The invariant sph_slab.cu rests on, replayed in numpy: with a z-slowest flatten and a stable
+    sort, a rank's boundary layer and its neighbour's ghost layer are contiguous index ranges holding
+    the same particles in the same order, so a halo refresh is a plain range copy."""
+    rng = np.random.default_rng(3)
+    nx, ny, nz, h = 7, 5, 12, 0.04
+    n = 6000
+    x = rng.uniform(0, [nx * h, ny * h, nz * h], size=(n, 3)).astype(np.float32)
+    uid = np.arange(n)
+    cell = np.clip((x / np.float32(h)).astype(np.int64), 0, [nx - 1, ny - 1, nz - 1])
+    flat = (cell[:, 2] * ny + cell[:, 1]) * nx + cell[:, 0]
+    z_cut = 6                                               # rank 0 owns layers [0, 6), rank 1 [6, 12)
+
+    def local_order(owned_mask, ghost_mask, prev_order):
+        """pre-sort local array = previously sorted owned particles, then the imported ghosts in the
+        sender's pre-sort order; the sort is a stable sort by cell."""
+        ids = np.concatenate([prev_order[owned_mask[prev_order]], ghost_mask])
+        return ids[np.argsort(flat[ids], kind="stable")]
+
+    own0, own1 = cell[:, 2] < z_cut, cell[:, 2] >= z_cut
+    prev0, prev1 = rng.permutation(n), rng.permutation(n)   # arbitrary previous orders on both ranks
+    send0 = prev0[(own0 & (cell[:, 2] == z_cut - 1))[prev0]]   # rank 0's boundary layer in ITS pre-sort order
+    send1 = prev1[(own1 & (cell[:, 2] == z_cut))[prev1]]
+    order0 = local_order(own0, send1, prev0)
+    order1 = local_order(own1, send0, prev1)
+    # rank 0: [owned ...][ghost layer z_cut]; its top boundary layer is the tail of the owned range
+    lay0 = cell[order0, 2]
+    assert np.all(np.diff(lay0) >= 0)
+    top0 = order0[lay0 == z_cut - 1]
+    ghost0 = order0[lay0 == z_cut]
+    lay1 = cell[order1, 2]
+    bottom1 = order1[lay1 == z_cut]
+    ghost1 = order1[lay1 == z_cut - 1]
+    assert np.array_equal(uid[top0], uid[ghost1])           # rank 0's send range == rank 1's ghost range
+    assert np.array_equal(uid[bottom1], uid[ghost0])
+    # contiguity: each of these sets is one index range of the sorted local array
+    for order, layer in ((order0, z_cut - 1), (order0, z_cut), (order1, z_cut), (order1, z_cut - 1)):
+        idx = np.nonzero(cell[order, 2] == layer)[0]
+        assert idx.size and idx[-1] - idx[0] + 1 == idx.size
