@@ -193,7 +193,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     lib = oracle_library()
-    cores = host_cores()
+    cores = int(os.environ.get("OMP_NUM_THREADS", host_cores()))   # the OpenMP team size actually used
     t0 = time.perf_counter()
     sc = dam_break_scene("dfsph")
     c, s = make_sim(sc, lib)
@@ -423,6 +423,9 @@ def main():
         os.environ.setdefault("OMP_PROC_BIND", "spread")
         os.environ.setdefault("OMP_PLACES", "cores")
         os.environ.setdefault("OMP_DYNAMIC", "false")
+        # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is one process that should use the host
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1 or "OMP_NUM_THREADS" not in os.environ:
+            os.environ["OMP_NUM_THREADS"] = str(host_cores())
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
