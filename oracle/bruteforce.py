@@ -5,7 +5,8 @@ TEST INFRASTRUCTURE ONLY — imported by tests/ to validate oracle/sph_oracle.cp
 oracle or the CUDA path: dense pair matrices instead of a grid, f64 instead of f32, formulas
 written from the reference's Python (paths relative to the reference checkout).
 
-PARITY UNPINNED (see oracle/sph_oracle.cpp): the reference ships no golden vectors.
+The reference ships no golden vectors; see oracle/sph_oracle.cpp for how the oracle is pinned
+(reference sources stepped on a Taichi emulation, tests/test_ref_golden.py).
 """
 import numpy as np
 

@@ -1,12 +1,19 @@
 // sph_oracle.cpp — CPU restatement of the reference's SPH hot path.  TEST INFRASTRUCTURE ONLY.
 //
-// PARITY UNPINNED: the reference (jason-huang03/SPH_Project @ 2a97e63) ships no tests, golden
-// vectors or fixtures for this path, and its implementation (Taichi kernels) cannot be imported
-// or compiled in this image (taichi / pybullet / trimesh absent, no network).  This file restates
-// the reference's algorithm function by function (each citing the file:line it follows) and is
-// pinned instead by (i) closed-form known answers (tests/test_oracle_kat.py), (ii) an independent
-// O(N^2) numpy restatement of the same formulas (oracle/bruteforce.py) and (iii) the scene-count
-// known answers of SURVEY.md 8(c).
+// PARITY PINNED AGAINST THE REFERENCE'S OWN PYTHON SOURCES, with one caveat.  The reference
+// (jason-huang03/SPH_Project @ 2a97e63) ships no tests, golden vectors or fixtures, and Taichi /
+// pybullet / trimesh cannot be installed in this image, so the real Taichi runtime never ran here.
+// Instead tests/golden/make_ref_golden.py imports /root/reference/SPH in place and steps it on
+// tests/golden/ref_shim, a small emulation of the Taichi API (kernel bodies executed as serial Python
+// on f32 numpy scalars).  The committed fixtures tests/golden/ref_*.npz hold its state after prepare()
+// and after every step for six tiny WCSPH / PCISPH / DFSPH scenes (domain box, over-dense blocks that
+// make the pressure solvers iterate, implicit viscosity, emitter); tests/test_ref_golden.py checks this
+// file against them: insertion lattice and integer fields bit for bit, every float field within 2e-5
+// of its scale (positions 2e-7), solver iteration counts exactly.  The caveat: Taichi's code
+// generation (fast-math, fma contraction, pow / inverse lowering, atomic order) is emulated, not run.
+// Further pins: (i) closed-form known answers (tests/test_oracle_kat.py), (ii) an independent O(N^2)
+// numpy restatement of the same formulas (oracle/bruteforce.py), (iii) the scene-count known answers
+// of SURVEY.md 8(c).
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library.  The product (sph_project_b200) never does.

@@ -1,0 +1,139 @@
+"""Golden vectors from the REFERENCE'S OWN PYTHON SOURCES, executed in this container.
+
+    python tests/golden/make_ref_golden.py [case ...]        (needs /root/reference; minutes per case)
+
+Taichi, pybullet and trimesh cannot be installed offline, so the reference (/root/reference/SPH, imported
+in place, never copied) runs on tests/golden/ref_shim: a small emulation of the Taichi API that executes
+the `@ti.kernel` / `@ti.func` bodies as serial Python with f32 numpy scalars (see its docstring for what
+that does and does not reproduce).  The scenes are tiny (a few hundred particles) because every
+floating-point operation is an interpreted numpy call.
+
+Each case writes tests/golden/ref_<case>.npz: the scene (JSON), the state after `prepare()` and after
+every step in a canonical particle order (lexicographic in the insertion position, which both sides keep),
+and the solver iteration counts parsed from the reference's own log lines.  tests/test_ref_golden.py
+checks the CPU oracle and (on a GPU) the CUDA path against them.
+"""
+import contextlib
+import io
+import json
+import os
+import re
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = "/root/reference"
+
+
+def scene(method, dt=1e-3, viscosity_method="standard", spacing=0.09, velocity=(0.0, -1.0, 0.0), g_upper=None,
+          block_end=(0.8, 0.85, 0.8), viscosity=0.05, viscosity_b=0.02, add_box=True, domain_end=1.6):
+    cfg = {"domainStart": [0.0, 0.0, 0.0], "domainEnd": [domain_end] * 3, "particleRadius": 0.05,
+           "particleSpacing": spacing, "addDomainBox": add_box, "density0": 1000, "gravitation": [0.0, -9.81, 0.0],
+           "simulationMethod": method, "viscosityMethod": viscosity_method, "timeStepSize": dt,
+           "viscosity": viscosity, "viscosity_b": viscosity_b, "exportFrame": False, "exportPly": False, "exportObj": False}
+    if g_upper is not None:
+        cfg["gravitationUpper"] = g_upper
+    block = {"objectId": 0, "start": [0.35, 0.3, 0.35], "end": list(block_end), "translation": [0.0, 0.0, 0.0],
+             "scale": [1, 1, 1], "velocity": list(velocity), "density": 1000.0, "color": [50, 100, 200], "entryTime": -1.0}
+    return {"Configuration": cfg, "FluidBlocks": [block]}
+
+
+CASES = {
+    # name: (scene kwargs, steps).  spacing 0.08 packs the block 1.56x over rest density so that the pressure
+    # solvers iterate; 0.09 is a gentle 1.1x.  domain_end 1.7 keeps the 0.08-spaced box out of the last cell layer,
+    # whose neighbour walk reads grid_num_particles out of bounds upstream (base_container.py:553-557)
+    "dfsph": (dict(method="dfsph", spacing=0.08, domain_end=1.7), 3),
+    "dfsph_gentle": (dict(method="dfsph"), 3),
+    "wcsph": (dict(method="wcsph", dt=5e-4), 4),
+    "pcisph": (dict(method="pcisph", dt=1e-3, spacing=0.08, domain_end=1.7), 3),
+    "dfsph_implicit": (dict(method="dfsph", viscosity_method="implicit", viscosity=50.0, viscosity_b=20.0), 2),
+    # no domain box: its particles carry object id -1 after init_object_id (base_solver.py:680-684), which the
+    # emitter branch of update_fluid_position would use as an out-of-bounds index (base_solver.py:660-663)
+    "dfsph_emitter": (dict(method="dfsph", g_upper=0.7, add_box=False), 3),
+}
+
+STATE_FIELDS = ("particle_positions", "particle_velocities", "particle_densities", "particle_pressures",
+                "particle_accelerations", "particle_rest_volumes", "particle_masses", "particle_materials",
+                "particle_object_ids", "particle_is_dynamic")
+EXTRA_FIELDS = {"dfsph": ("particle_dfsph_alphas", "particle_densities_star", "particle_densities_derivatives"),
+                "pcisph": ("particle_densities_star",), "wcsph": ()}
+
+
+def import_reference():
+    sys.path[:] = [os.path.join(HERE, "ref_shim"), REFERENCE] + [p for p in sys.path
+                                                                 if os.path.abspath(p or ".") != os.path.dirname(os.path.dirname(HERE))]
+    import taichi as ti
+    assert "ref_shim" in ti.__file__
+    from SPH.utils import SimConfig
+    from SPH.containers import DFSPHContainer, WCSPHContainer, PCISPHContainer
+    from SPH.fluid_solvers import DFSPHSolver, WCSPHSolver, PCISPHSolver
+    import SPH
+    assert SPH.__path__[0].startswith(REFERENCE), SPH.__path__
+    return SimConfig, {"dfsph": (DFSPHContainer, DFSPHSolver), "wcsph": (WCSPHContainer, WCSPHSolver),
+                       "pcisph": (PCISPHContainer, PCISPHSolver)}
+
+
+def snapshot(container, method, order=None):
+    n = int(container.particle_num[None])
+    x0 = container.rigid_particle_original_positions.to_numpy()[:n]
+    perm = np.lexsort((x0[:, 2], x0[:, 1], x0[:, 0]))
+    out = {"x0": x0[perm]}
+    for name in STATE_FIELDS + EXTRA_FIELDS[method]:
+        out[name] = getattr(container, name).to_numpy()[:n][perm]
+    return out
+
+
+ITER_RE = {
+    "dfsph": re.compile(r"DFSPH - iterations: (\d+)"), "dfsph_v": re.compile(r"DFSPH - iteration V: (\d+)"),
+    "pcisph": re.compile(r"PCISPH - iteration: (\d+)"), "cg": re.compile(r"CG iteration:\s+(\d+)"),
+}
+
+
+def run_case(name):
+    kw, steps = CASES[name]
+    sc = scene(**kw)
+    method = kw["method"]
+    SimConfig, classes = import_reference()
+    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+        json.dump(sc, fh)
+    log = io.StringIO()
+    t0 = time.time()
+    with contextlib.redirect_stdout(log):
+        cfg = SimConfig(scene_file_path=fh.name)
+        C, S = classes[method]
+        container = C(cfg, GGUI=False)
+        solver = S(container)
+        solver.prepare()
+    os.unlink(fh.name)
+    out = {"scene": np.array(json.dumps(sc)), "steps": np.array(steps)}
+    for k, v in snapshot(container, method).items():
+        out["prepared_" + k] = v
+    if method == "pcisph":
+        out["pcisph_k"] = np.array(container.pcisph_k[None], dtype=np.float32)
+    print(f"[{name}] prepared {int(container.particle_num[None])} particles "
+          f"({int(container.fluid_particle_num[None])} fluid) in {time.time() - t0:.0f} s", flush=True)
+    iters = {k: [] for k in ITER_RE}
+    for s in range(steps):
+        log.seek(0); log.truncate()
+        t0 = time.time()
+        with contextlib.redirect_stdout(log):
+            solver.step()
+        text = log.getvalue()
+        for k, rx in ITER_RE.items():
+            iters[k].append(sum(int(m) for m in rx.findall(text)))
+        for k, v in snapshot(container, method).items():
+            if k in ("x0", "particle_object_ids", "particle_is_dynamic", "particle_masses"):
+                continue
+            out[f"step{s + 1}_" + k] = v
+        print(f"[{name}] step {s + 1}: {time.time() - t0:.0f} s  " + " ".join(f"{k}={v[-1]}" for k, v in iters.items()), flush=True)
+    for k, v in iters.items():
+        out["iterations_" + k] = np.array(v, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **out)
+
+
+if __name__ == "__main__":
+    for case in (sys.argv[1:] or list(CASES)):
+        run_case(case)
