@@ -29,7 +29,7 @@ REFERENCE = "/root/reference"
 
 
 def scene(method, dt=1e-3, viscosity_method="standard", spacing=0.09, velocity=(0.0, -1.0, 0.0), g_upper=None,
-          block_end=(0.8, 0.85, 0.8), viscosity=0.05, viscosity_b=0.02, add_box=True, domain_end=1.6):
+          block_end=(0.8, 0.85, 0.8), viscosity=0.05, viscosity_b=0.02, add_box=True, domain_end=1.6, rigid=False, late_block=False):
     cfg = {"domainStart": [0.0, 0.0, 0.0], "domainEnd": [domain_end] * 3, "particleRadius": 0.05,
            "particleSpacing": spacing, "addDomainBox": add_box, "density0": 1000, "gravitation": [0.0, -9.81, 0.0],
            "simulationMethod": method, "viscosityMethod": viscosity_method, "timeStepSize": dt,
@@ -38,7 +38,41 @@ def scene(method, dt=1e-3, viscosity_method="standard", spacing=0.09, velocity=(
         cfg["gravitationUpper"] = g_upper
     block = {"objectId": 0, "start": [0.35, 0.3, 0.35], "end": list(block_end), "translation": [0.0, 0.0, 0.0],
              "scale": [1, 1, 1], "velocity": list(velocity), "density": 1000.0, "color": [50, 100, 200], "entryTime": -1.0}
-    return {"Configuration": cfg, "FluidBlocks": [block]}
+    out = {"Configuration": cfg, "FluidBlocks": [block]}
+    if late_block:     # a second block that enters while the run is under way (insert_object is called every step)
+        out["FluidBlocks"].append({"objectId": 1, "start": [0.9, 0.5, 0.9], "end": [1.2, 0.8, 1.2], "translation": [0.0, 0.0, 0.0],
+                                   "scale": [1, 1, 1], "velocity": [0.0, -2.0, 0.0], "density": 1000.0, "color": [200, 50, 50],
+                                   "entryTime": 0.0008})
+    if rigid:
+        # a light dynamic cube (side 0.3) dropped onto the block; geometryFile is filled in per run (temp dir)
+        out["RigidBodies"] = [{"objectId": 1, "geometryFile": "cube.obj", "translation": [0.575, 1.10, 0.575],
+                               "rotationAxis": [0.0, 1.0, 0.0], "rotationAngle": 0.0, "scale": [0.3, 0.3, 0.3],
+                               "velocity": [0.3, -1.0, 0.0], "density": 500.0, "color": [200, 100, 50], "isDynamic": True,
+                               "entryTime": -1.0}]
+    return out
+
+
+CUBE_OBJ = """v -0.5 -0.5 -0.5
+v 0.5 -0.5 -0.5
+v 0.5 0.5 -0.5
+v -0.5 0.5 -0.5
+v -0.5 -0.5 0.5
+v 0.5 -0.5 0.5
+v 0.5 0.5 0.5
+v -0.5 0.5 0.5
+f 1 3 2
+f 1 4 3
+f 5 6 7
+f 5 7 8
+f 1 2 6
+f 1 6 5
+f 4 7 3
+f 4 8 7
+f 1 5 8
+f 1 8 4
+f 2 3 7
+f 2 7 6
+"""
 
 
 CASES = {
@@ -53,6 +87,11 @@ CASES = {
     # no domain box: its particles carry object id -1 after init_object_id (base_solver.py:680-684), which the
     # emitter branch of update_fluid_position would use as an out-of-bounds index (base_solver.py:660-663)
     "dfsph_emitter": (dict(method="dfsph", g_upper=0.7, add_box=False), 3),
+    # fluid <-> dynamic rigid body coupling; the rigid dynamics are ref_shim/free_body.py on both sides, not Bullet
+    "dfsph_rigid": (dict(method="dfsph", rigid=True), 3),
+    "wcsph_rigid": (dict(method="wcsph", dt=5e-4, rigid=True), 3),
+    "pcisph_rigid": (dict(method="pcisph", rigid=True), 2),
+    "wcsph_late_block": (dict(method="wcsph", dt=5e-4, late_block=True), 4),
 }
 
 STATE_FIELDS = ("particle_positions", "particle_velocities", "particle_densities", "particle_pressures",
@@ -97,7 +136,13 @@ def run_case(name):
     sc = scene(**kw)
     method = kw["method"]
     SimConfig, classes = import_reference()
-    with tempfile.NamedTemporaryFile("w", suffix=".json", delete=False) as fh:
+    rigid = "RigidBodies" in sc
+    tmpdir = tempfile.mkdtemp()
+    if rigid:
+        sc["RigidBodies"][0]["geometryFile"] = os.path.join(tmpdir, "cube.obj")
+        with open(sc["RigidBodies"][0]["geometryFile"], "w") as fh:
+            fh.write(CUBE_OBJ)
+    with open(os.path.join(tmpdir, "scene.json"), "w") as fh:
         json.dump(sc, fh)
     log = io.StringIO()
     t0 = time.time()
@@ -107,8 +152,21 @@ def run_case(name):
         container = C(cfg, GGUI=False)
         solver = S(container)
         solver.prepare()
-    os.unlink(fh.name)
-    out = {"scene": np.array(json.dumps(sc)), "steps": np.array(steps)}
+    import copy
+    import shutil
+    shutil.rmtree(tmpdir)
+    sc_out = copy.deepcopy(sc)
+    for body in sc_out.get("RigidBodies", []):      # SimConfig keeps the dict: drop what load_rigid_body attached
+        for key in ("mesh", "restPosition", "restCenterOfMass", "particleNum", "voxelizedPoints"):
+            body.pop(key, None)
+        body["geometryFile"] = "cube.obj"
+    for blk in sc_out["FluidBlocks"]:
+        blk.pop("particleNum", None)
+    out = {"scene": np.array(json.dumps(sc_out)), "steps": np.array(steps)}
+    if rigid:
+        import pybullet
+        out["cube_obj"] = np.array(CUBE_OBJ)
+        out["rigid_mass"] = np.array(container.rigid_body_masses[1], dtype=np.float32)
     for k, v in snapshot(container, method).items():
         out["prepared_" + k] = v
     if method == "pcisph":
@@ -125,9 +183,14 @@ def run_case(name):
         for k, rx in ITER_RE.items():
             iters[k].append(sum(int(m) for m in rx.findall(text)))
         for k, v in snapshot(container, method).items():
-            if k in ("x0", "particle_object_ids", "particle_is_dynamic", "particle_masses"):
+            if k in ("particle_object_ids", "particle_is_dynamic", "particle_masses"):
                 continue
             out[f"step{s + 1}_" + k] = v
+        if rigid:
+            F, T = pybullet.world.log[-1][0]
+            out[f"step{s + 1}_rigid_force"], out[f"step{s + 1}_rigid_torque"] = F, T
+            for key in ("centers_of_mass", "rotations", "velocities", "angular_velocities"):
+                out[f"step{s + 1}_rigid_body_{key}"] = getattr(container, "rigid_body_" + key).to_numpy()[1]
         print(f"[{name}] step {s + 1}: {time.time() - t0:.0f} s  " + " ".join(f"{k}={v[-1]}" for k, v in iters.items()), flush=True)
     for k, v in iters.items():
         out["iterations_" + k] = np.array(v, dtype=np.int64)
