@@ -35,6 +35,8 @@
 #include "../include/sph_b200.h"
 
 #include <algorithm>
+#include <parallel/algorithm>
+#include <type_traits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -208,37 +210,50 @@ int fail(SphHandle* h, int code, const char* msg) {
 }
 
 // init_grid + PrefixSumExecutor.run + reorder_particles (base_container.py:495-547)
+//
+// The reference's reorder is a counting sort whose in-cell order, run serially, is ascending particle
+// index (descending loop + atomic_sub, :510-515).  The same permutation is obtained here by sorting the
+// unique 64-bit keys (cell << 32 | index), which parallelises (libstdc++ parallel mode) -- the serial
+// counting sort was the Amdahl bottleneck of the CPU baseline on many-core hosts.
 void prepare_neighborhood_search(SphHandle& s) {
     const int N = s.N;
-    std::vector<int32_t> count(s.ncell, 0);
+    std::vector<uint64_t> keys((size_t)N);
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < N; i++) {
         int c[3];
         s.pos_to_index(s.x[i], c);
         // keep indices inside the array like a well-defined run of the reference would
         for (int d = 0; d < 3; d++) c[d] = std::min(std::max(c[d], 0), s.P.grid_num[d] - 1);
         s.grid_id[i] = s.flatten(c);
-        count[s.grid_id[i]]++;
+        keys[i] = ((uint64_t)(uint32_t)s.grid_id[i] << 32) | (uint32_t)i;
     }
-    // inclusive scan (:546)
-    int acc = 0;
+    __gnu_parallel::sort(keys.begin(), keys.end());
+    // per-cell counts -> inclusive scan (:546): cell c ends where the last key of a cell <= c sits
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < s.ncell; c++) s.cell_scan[c] = 0;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < N; k++) {
+        int cell = (int)(keys[k] >> 32);
+        if (k + 1 == N || (int)(keys[k + 1] >> 32) != cell) s.cell_scan[cell] = k + 1;
+    }
+    int acc = 0;     // empty cells inherit the running end
     for (int c = 0; c < s.ncell; c++) {
-        acc += count[c];
-        s.cell_scan[c] = acc;
-    }
-    // stable counting sort == the reference's descending atomic_sub loop run serially (:510-515)
-    std::vector<int32_t> temp(count), new_index(N);
-    for (int i = 0; i < N; i++) {
-        int p_i = N - 1 - i;
-        int gid = s.grid_id[p_i];
-        int base = gid - 1 >= 0 ? s.cell_scan[gid - 1] : 0;
-        new_index[p_i] = (temp[gid]--) - 1 + base;
+        if (s.cell_scan[c] == 0) s.cell_scan[c] = acc;
+        acc = s.cell_scan[c];
     }
     // permute exactly the fields of :517-542 (+ uid); everything else stays index-bound
     auto permute = [&](auto& vec, int comps) {
-        auto buf = vec;
-        for (int i = 0; i < N; i++)
-            for (int c = 0; c < comps; c++) buf[(size_t)new_index[i] * comps + c] = vec[(size_t)i * comps + c];
-        std::copy(buf.begin(), buf.begin() + (size_t)N * comps, vec.begin());
+        using T = typename std::remove_reference<decltype(vec)>::type::value_type;
+        std::vector<T> buf(vec.size());
+#pragma omp parallel for schedule(static)
+        for (int k = 0; k < N; k++) {
+            size_t src = (size_t)(uint32_t)keys[k];
+            for (int c = 0; c < comps; c++) buf[(size_t)k * comps + c] = vec[src * comps + c];
+        }
+        size_t live = (size_t)N * comps;
+#pragma omp parallel for schedule(static)
+        for (long long q = (long long)live; q < (long long)vec.size(); q++) buf[q] = vec[q];
+        vec.swap(buf);
     };
     permute(s.grid_id, 1);
     permute(s.object_id, 1);
