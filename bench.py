@@ -109,10 +109,25 @@ def oracle_library():
 
 
 def host_cores():
+    """Usable host threads: the affinity mask, capped by a cgroup CPU quota when the container has one
+    (an OpenMP team larger than the quota only oversubscribes)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]            # cgroup v2
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())           # cgroup v1
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return n
 
 
 def cpu_model():
@@ -374,7 +389,7 @@ def run_gpu(args, rank, world, local_rank):
         one = time.perf_counter() - t0
         k = int(min(max(12.0 / max(one, 1e-3), 2), 40))      # about 12 s of CPU work
         v, dt, st2 = time_cpu(s2, c2, k, 0)
-        cpu = {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port", "cpu": cpu_model(),
+        cpu = {"value": v, "unit": UNIT, "cores": int(os.environ.get("OMP_NUM_THREADS", host_cores())), "kind": "port", "cpu": cpu_model(),
                "sample": f"full workload ({c2.fluid_particle_num[None]} fluid + {c2.particle_num[None] - c2.fluid_particle_num[None]} boundary), "
                          f"{k} steps after 2 warm-up steps from the initial lattice, early window ({dt:.1f} s of CPU work, "
                          f"{st2.total_dfsph_iterations / k:.1f}+{st2.total_dfsph_iterations_v / k:.1f} solver iterations/step)"}
@@ -426,6 +441,13 @@ def main():
         # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is one process that should use the host
         if int(os.environ.get("WORLD_SIZE", "1")) > 1 or "OMP_NUM_THREADS" not in os.environ:
             os.environ["OMP_NUM_THREADS"] = str(host_cores())
+    elif args.impl == "b200" and int(os.environ.get("WORLD_SIZE", "1")) == 1 and "OMP_NUM_THREADS" not in os.environ:
+        # single-process GPU arm: its cpu_baseline leg should not oversubscribe a cgroup CPU quota
+        try:
+            if host_cores() < len(os.sched_getaffinity(0)):
+                os.environ["OMP_NUM_THREADS"] = str(host_cores())
+        except AttributeError:
+            pass
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
