@@ -29,7 +29,7 @@ REFERENCE = "/root/reference"
 
 
 def scene(method, dt=1e-3, viscosity_method="standard", spacing=0.09, velocity=(0.0, -1.0, 0.0), g_upper=None,
-          block_end=(0.8, 0.85, 0.8), viscosity=0.05, viscosity_b=0.02, add_box=True, domain_end=1.6, rigid=False, late_block=False):
+          block_end=(0.8, 0.85, 0.8), viscosity=0.05, viscosity_b=0.02, add_box=True, domain_end=1.6, rigid=False, late_block=False, mesh_bodies=False):
     cfg = {"domainStart": [0.0, 0.0, 0.0], "domainEnd": [domain_end] * 3, "particleRadius": 0.05,
            "particleSpacing": spacing, "addDomainBox": add_box, "density0": 1000, "gravitation": [0.0, -9.81, 0.0],
            "simulationMethod": method, "viscosityMethod": viscosity_method, "timeStepSize": dt,
@@ -43,6 +43,15 @@ def scene(method, dt=1e-3, viscosity_method="standard", spacing=0.09, velocity=(
         out["FluidBlocks"].append({"objectId": 1, "start": [0.9, 0.5, 0.9], "end": [1.2, 0.8, 1.2], "translation": [0.0, 0.0, 0.0],
                                    "scale": [1, 1, 1], "velocity": [0.0, -2.0, 0.0], "density": 1000.0, "color": [200, 50, 50],
                                    "entryTime": 0.0008})
+    if mesh_bodies:
+        # a static, rotated rigid cube next to the block and a fluid body cut from a mesh (base_container.py:611-717)
+        out["RigidBodies"] = [{"objectId": 1, "geometryFile": "cube.obj", "translation": [1.05, 0.45, 0.6],
+                               "rotationAxis": [0.0, 1.0, 0.0], "rotationAngle": 30.0, "scale": [0.3, 0.3, 0.3],
+                               "velocity": [0.0, 0.0, 0.0], "density": 1000.0, "color": [200, 100, 50], "isDynamic": False,
+                               "entryTime": -1.0}]
+        out["FluidBodies"] = [{"objectId": 2, "geometryFile": "cube.obj", "translation": [0.6, 1.1, 0.6],
+                               "rotationAxis": [0.0, 0.0, 1.0], "rotationAngle": 20.0, "scale": [0.3, 0.25, 0.3],
+                               "velocity": [0.0, -1.5, 0.0], "density": 1000.0, "color": [50, 200, 50], "entryTime": -1.0}]
     if rigid:
         # a light dynamic cube (side 0.3) dropped onto the block; geometryFile is filled in per run (temp dir)
         out["RigidBodies"] = [{"objectId": 1, "geometryFile": "cube.obj", "translation": [0.575, 1.10, 0.575],
@@ -92,6 +101,9 @@ CASES = {
     "wcsph_rigid": (dict(method="wcsph", dt=5e-4, rigid=True), 3),
     "pcisph_rigid": (dict(method="pcisph", rigid=True), 2),
     "wcsph_late_block": (dict(method="wcsph", dt=5e-4, late_block=True), 4),
+    # mesh bodies: trimesh is replaced by this repository's voxeliser on both sides (ref_shim/trimesh.py), which pins
+    # the placement / lattice / insertion logic around it and the static-body kernels, not the voxeliser itself
+    "dfsph_mesh_bodies": (dict(method="dfsph", mesh_bodies=True), 2),
 }
 
 STATE_FIELDS = ("particle_positions", "particle_velocities", "particle_densities", "particle_pressures",
@@ -136,11 +148,12 @@ def run_case(name):
     sc = scene(**kw)
     method = kw["method"]
     SimConfig, classes = import_reference()
-    rigid = "RigidBodies" in sc
+    meshes = sc.get("RigidBodies", []) + sc.get("FluidBodies", [])
+    rigid = any(b.get("isDynamic") for b in sc.get("RigidBodies", []))
     tmpdir = tempfile.mkdtemp()
-    if rigid:
-        sc["RigidBodies"][0]["geometryFile"] = os.path.join(tmpdir, "cube.obj")
-        with open(sc["RigidBodies"][0]["geometryFile"], "w") as fh:
+    for body in meshes:
+        body["geometryFile"] = os.path.join(tmpdir, "cube.obj")
+        with open(body["geometryFile"], "w") as fh:
             fh.write(CUBE_OBJ)
     with open(os.path.join(tmpdir, "scene.json"), "w") as fh:
         json.dump(sc, fh)
@@ -156,16 +169,17 @@ def run_case(name):
     import shutil
     shutil.rmtree(tmpdir)
     sc_out = copy.deepcopy(sc)
-    for body in sc_out.get("RigidBodies", []):      # SimConfig keeps the dict: drop what load_rigid_body attached
+    for body in sc_out.get("RigidBodies", []) + sc_out.get("FluidBodies", []):      # SimConfig keeps the dict: drop what load_rigid_body attached
         for key in ("mesh", "restPosition", "restCenterOfMass", "particleNum", "voxelizedPoints"):
             body.pop(key, None)
         body["geometryFile"] = "cube.obj"
     for blk in sc_out["FluidBlocks"]:
         blk.pop("particleNum", None)
     out = {"scene": np.array(json.dumps(sc_out)), "steps": np.array(steps)}
+    if meshes:
+        out["cube_obj"] = np.array(CUBE_OBJ)
     if rigid:
         import pybullet
-        out["cube_obj"] = np.array(CUBE_OBJ)
         out["rigid_mass"] = np.array(container.rigid_body_masses[1], dtype=np.float32)
     for k, v in snapshot(container, method).items():
         out["prepared_" + k] = v

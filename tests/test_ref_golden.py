@@ -35,7 +35,8 @@ def load(name, tmp_path=None):
         path = os.path.join(str(tmp_path), "cube.obj")
         with open(path, "w") as fh:
             fh.write(str(g["cube_obj"]))
-        sc["RigidBodies"][0]["geometryFile"] = path
+        for body in sc.get("RigidBodies", []) + sc.get("FluidBodies", []):
+            body["geometryFile"] = path
     return g, sc
 
 
@@ -93,7 +94,7 @@ class FreeBodyAdapter:
 
 def build(sc, lib, g):
     """(container, solver) prepared like the fixture's reference run."""
-    if "cube_obj" not in g.files:
+    if "rigid_mass" not in g.files:          # no dynamic body: the stock rigid solver has nothing to do
         return make_sim(sc, lib)
     c, s = make_sim(sc, lib, prepare=False)
     s.rigid_solver = FreeBodyAdapter(c, s.g, s.dt[None])
@@ -182,14 +183,17 @@ def test_oracle_matches_reference_sources(name, tmp_path):
         assert counts[:3] == iteration_counts(g, k)[:3], f"step {k + 1}"
         assert abs(counts[3] - iteration_counts(g, k)[3]) <= 1, f"step {k + 1}: CG iterations"
         compare(c, g, f"step{k + 1}_", rtol=2e-5)
-        if "cube_obj" in g.files:
+        if "rigid_mass" in g.files:
             compare_rigid(c, s, g, k + 1, rtol=2e-5)
 
 
+NEXT_ROWS = [n for n in CASES if n.endswith("_rigid") or n.endswith("_mesh_bodies")]   # SURVEY 8(f2, f3)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", [n for n in CASES if not n.endswith("_rigid")])
-def test_cuda_matches_reference_sources(name):
-    g, sc = load(name)
+@pytest.mark.parametrize("name", [n for n in CASES if n not in NEXT_ROWS])
+def test_cuda_matches_reference_sources(name, tmp_path):
+    g, sc = load(name, tmp_path)
     c, s = make_sim(sc)
     compare(c, g, "prepared_", rtol=1e-5, only=INT_FIELDS + ("particle_positions", "particle_velocities", "particle_densities",
                                                           "particle_rest_volumes", "particle_masses", "particle_dfsph_alphas"))
@@ -202,8 +206,8 @@ def test_cuda_matches_reference_sources(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_next          # dynamic rigid bodies are a SURVEY 8(f3) "next" row: opt in with SPH_RUN_GPU_NEXT=1
-@pytest.mark.parametrize("name", [n for n in CASES if n.endswith("_rigid")])
+@pytest.mark.gpu_next          # mesh bodies / dynamic rigid bodies are SURVEY 8(f2, f3) "next" rows, not yet run on
+@pytest.mark.parametrize("name", NEXT_ROWS)   # hardware: opt in with SPH_RUN_GPU_NEXT=1
 def test_cuda_rigid_coupling_matches_reference_sources(name, tmp_path):
     g, sc = load(name, tmp_path)
     c, s = build(sc, None, g)
@@ -214,4 +218,5 @@ def test_cuda_rigid_coupling_matches_reference_sources(name, tmp_path):
         assert all(abs(a - b) <= 1 for a, b in zip(counts[:3], ref[:3])), (k, counts, ref)
         compare(c, g, f"step{k + 1}_", rtol=1e-4, only=("particle_positions", "particle_materials"))
         compare(c, g, f"step{k + 1}_", rtol=1e-3, only=("particle_velocities", "particle_densities"))
-        compare_rigid(c, s, g, k + 1, rtol=1e-3)
+        if "rigid_mass" in g.files:
+            compare_rigid(c, s, g, k + 1, rtol=1e-3)
