@@ -350,6 +350,19 @@ def run_gpu(args, rank, world, local_rank):
                 "share_of_kernel_time": dom_ms / total_kernel_ms, "accepted_pairs": n_pairs,
                 "note": "list-based sweeps are bound by L1 gather throughput (ncu: l1tex 80-91 % of peak, ~1 sector per pair), not by HBM; frac = algorithmic bytes / time / measured HBM peak",
                 "profiled_pass_ms_per_step": prof_ms / args.steps, "kernels": kernels}
+    # secondary figures SURVEY 8(d) asks for next to the HBM fraction of a neighbour sweep: the pair-model FP32
+    # rate and the L1 gather rate (one 32-byte record per accepted pair; a scattered 32-lane gather costs one L1
+    # tag lookup per distinct 128-byte line, at most one per clock per SM)
+    sm_mhz = (clock_info or {}).get("sm_mhz") or 1965.0
+    if dom_name.split("<")[0] in LIST_CONSUMERS and n_pairs:
+        t_s = dom_ms / dom_launches * 1e-3
+        flops = n_pairs * 25.0                                    # f_task of the DFSPH / pressure / viscosity tasks
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        roofline["fp32_pair_model"] = {"flops_per_launch": flops, "achieved_TFLOPs": flops / t_s / 1e12, "peak_TFLOPs": fp32_peak,
+                                       "frac": flops / t_s / 1e12 / fp32_peak,
+                                       "peak_source": "148 SMs x 128 FMA lanes x 2 x sampled SM clock (nominal, not measured)"}
+        roofline["l1_gather"] = {"pairs_per_clk_per_sm": n_pairs / (t_s * 148 * sm_mhz * 1e6), "bound": 1.0,
+                                 "what": "accepted pairs per SM clock vs one L1 line lookup per clock per SM (every pair gathers one 32-byte record from a different line)"}
 
     # ---- e2e: host buffers in and out every step, through the C ABI ----
     from sph_project_b200._native import F
