@@ -65,6 +65,47 @@ def algo_bytes(kernel, n_total, n_pairs):
     return b
 
 
+def roofline_report(prof, n_rows, n_pairs, clock_info, hbm_peak, peak_src, profiled_ms_per_step):
+    """The `roofline` object of the JSON line from one profiled pass.
+    prof: {kernel name: (launches, total ms)} (sph_profile_read); n_rows: particles a launch iterates;
+    n_pairs: accepted (fluid-row) neighbour pairs; hbm_peak in GB/s."""
+    total_kernel_ms = sum(v[1] for v in prof.values())
+    top = sorted(prof.items(), key=lambda kv: -kv[1][1])
+    kernels = []
+    for k, v in top[:10]:
+        ab = algo_bytes(k, n_rows, n_pairs)
+        kernels.append({"name": k, "launches": int(v[0]), "ms_per_launch": v[1] / v[0], "share": v[1] / total_kernel_ms,
+                        "algo_GBps": (ab / (v[1] / v[0] * 1e-3) / 1e9) if ab else None})
+    dom_name, (dom_launches, dom_ms) = top[0]
+    dom_bytes = algo_bytes(dom_name, n_rows, n_pairs) or 0
+    achieved = dom_bytes / (dom_ms / dom_launches * 1e-3) / 1e9
+    traffic = None   # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["dram_bytes_per_launch"].get(dom_name.split("<")[0])
+    except (OSError, KeyError, ValueError):
+        pass
+    roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms / dom_launches,
+                "share_of_kernel_time": dom_ms / total_kernel_ms, "accepted_pairs": n_pairs,
+                "note": "list-based sweeps are bound by L1 gather throughput (ncu: l1tex 80-91 % of peak, ~1 sector per pair), not by HBM; frac = algorithmic bytes / time / measured HBM peak",
+                "profiled_pass_ms_per_step": profiled_ms_per_step, "kernels": kernels}
+    # secondary figures SURVEY 8(d) asks for next to the HBM fraction of a neighbour sweep: the pair-model FP32
+    # rate and the L1 gather rate (one 32-byte record per accepted pair; a scattered 32-lane gather costs one L1
+    # tag lookup per distinct 128-byte line, at most one per clock per SM)
+    sm_mhz = (clock_info or {}).get("sm_mhz") or 1965.0
+    if dom_name.split("<")[0] in LIST_CONSUMERS and n_pairs:
+        t_s = dom_ms / dom_launches * 1e-3
+        flops = n_pairs * 25.0                                    # f_task of the DFSPH / pressure / viscosity tasks
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        roofline["fp32_pair_model"] = {"flops_per_launch": flops, "achieved_TFLOPs": flops / t_s / 1e12, "peak_TFLOPs": fp32_peak,
+                                       "frac": flops / t_s / 1e12 / fp32_peak,
+                                       "peak_source": "148 SMs x 128 FMA lanes x 2 x sampled SM clock (nominal, not measured)"}
+        roofline["l1_gather"] = {"pairs_per_clk_per_sm": n_pairs / (t_s * 148 * sm_mhz * 1e6), "bound": 1.0,
+                                 "what": "accepted pairs per SM clock vs one L1 line lookup per clock per SM (every pair gathers one 32-byte record from a different line)"}
+    return roofline
+
+
 def dam_break_scene(method="dfsph", scale=1.0, n_slabs=1):
     """final_scene0.json geometry (reference data/scenes/final_scene0.json:5-16,52-63), no RigidBodies.
     scale < 1 shrinks every length (bounded CPU sample); n_slabs > 1 stretches the block and the
@@ -324,45 +365,12 @@ def run_gpu(args, rank, world, local_rank):
     prof = eng.profile_read()
     eng.profile_enable(False)
     prof_ms = evp0.elapsed_time(evp1)
-    total_kernel_ms = sum(v[1] for v in prof.values())
-    top = sorted(prof.items(), key=lambda kv: -kv[1][1])
     from sph_project_b200._native import F as _F
     n_local = int(container.particle_num[None])
     mat_now = container.particle_materials.to_numpy(n_local)
     n_pairs = int(eng.get_field(_F.NEIGHBOR_COUNT, n_local)[(mat_now == 1) & container.owned_mask()].sum())
     n_rows = n_local   # kernels of this rank stream this rank's particles
-    kernels = []
-    for k, v in top[:10]:
-        ab = algo_bytes(k, n_rows, n_pairs)
-        kernels.append({"name": k, "launches": int(v[0]), "ms_per_launch": v[1] / v[0], "share": v[1] / total_kernel_ms,
-                        "algo_GBps": (ab / (v[1] / v[0] * 1e-3) / 1e9) if ab else None})
-    dom_name, (dom_launches, dom_ms) = top[0]
-    dom_bytes = algo_bytes(dom_name, n_rows, n_pairs) or 0
-    achieved = dom_bytes / (dom_ms / dom_launches * 1e-3) / 1e9
-    traffic = None   # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))["dram_bytes_per_launch"].get(dom_name.split("<")[0])
-    except (OSError, KeyError, ValueError):
-        pass
-    roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms / dom_launches,
-                "share_of_kernel_time": dom_ms / total_kernel_ms, "accepted_pairs": n_pairs,
-                "note": "list-based sweeps are bound by L1 gather throughput (ncu: l1tex 80-91 % of peak, ~1 sector per pair), not by HBM; frac = algorithmic bytes / time / measured HBM peak",
-                "profiled_pass_ms_per_step": prof_ms / args.steps, "kernels": kernels}
-    # secondary figures SURVEY 8(d) asks for next to the HBM fraction of a neighbour sweep: the pair-model FP32
-    # rate and the L1 gather rate (one 32-byte record per accepted pair; a scattered 32-lane gather costs one L1
-    # tag lookup per distinct 128-byte line, at most one per clock per SM)
-    sm_mhz = (clock_info or {}).get("sm_mhz") or 1965.0
-    if dom_name.split("<")[0] in LIST_CONSUMERS and n_pairs:
-        t_s = dom_ms / dom_launches * 1e-3
-        flops = n_pairs * 25.0                                    # f_task of the DFSPH / pressure / viscosity tasks
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        roofline["fp32_pair_model"] = {"flops_per_launch": flops, "achieved_TFLOPs": flops / t_s / 1e12, "peak_TFLOPs": fp32_peak,
-                                       "frac": flops / t_s / 1e12 / fp32_peak,
-                                       "peak_source": "148 SMs x 128 FMA lanes x 2 x sampled SM clock (nominal, not measured)"}
-        roofline["l1_gather"] = {"pairs_per_clk_per_sm": n_pairs / (t_s * 148 * sm_mhz * 1e6), "bound": 1.0,
-                                 "what": "accepted pairs per SM clock vs one L1 line lookup per clock per SM (every pair gathers one 32-byte record from a different line)"}
+    roofline = roofline_report(prof, n_rows, n_pairs, clock_info, hbm_peak, peak_src, prof_ms / args.steps)
 
     # ---- e2e: host buffers in and out every step, through the C ABI ----
     from sph_project_b200._native import F
