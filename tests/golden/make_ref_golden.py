@@ -104,6 +104,9 @@ CASES = {
     # mesh bodies: trimesh is replaced by this repository's voxeliser on both sides (ref_shim/trimesh.py), which pins
     # the placement / lattice / insertion logic around it and the static-body kernels, not the voxeliser itself
     "dfsph_mesh_bodies": (dict(method="dfsph", mesh_bodies=True), 2),
+    # the solver / viscosity keys are independent (base_solver.py:25,195-200): BASELINE config C4's combination
+    "pcisph_implicit": (dict(method="pcisph", viscosity_method="implicit", viscosity=50.0, viscosity_b=20.0, spacing=0.085), 2),
+    "wcsph_implicit": (dict(method="wcsph", dt=5e-4, viscosity_method="implicit", viscosity=20.0, viscosity_b=20.0), 2),
 }
 
 STATE_FIELDS = ("particle_positions", "particle_velocities", "particle_densities", "particle_pressures",
