@@ -137,6 +137,10 @@ def snapshot(container, method, order=None):
     out = {"x0": x0[perm]}
     for name in STATE_FIELDS + EXTRA_FIELDS[method]:
         out[name] = getattr(container, name).to_numpy()[:n][perm]
+    # the sort structures of the last neighbourhood search (base_container.py:495-547): per-particle flat cell id
+    # (z-fastest flatten) and the inclusive scan of the per-cell counts
+    out["grid_ids"] = container.grid_ids.to_numpy()[:n][perm]
+    out["grid_num_particles"] = container.grid_num_particles.to_numpy()
     return out
 
 

@@ -160,6 +160,17 @@ def compare(container, g, prefix, rtol, only=None):
     return worst
 
 
+def compare_sort_structures(container, g, prefix):
+    """Flat cell id per particle and the inclusive scan of the per-cell counts, bit for bit (oracle only: the CUDA
+    path flattens x-fastest, which is not part of the reference's API)."""
+    if prefix + "grid_ids" not in g.files:
+        return
+    perm, _ = canonical(container)
+    n = container.particle_num[None]
+    assert np.array_equal(container.grid_ids.to_numpy(n)[perm], g[prefix + "grid_ids"]), prefix
+    assert np.array_equal(container.grid_num_particles.to_numpy(), g[prefix + "grid_num_particles"]), prefix
+
+
 def iteration_counts(g, k):
     return tuple(int(g[f"iterations_{key}"][k]) for key in ("dfsph", "dfsph_v", "pcisph", "cg"))
 
@@ -177,6 +188,7 @@ def test_oracle_matches_reference_sources(name, tmp_path):
     g, sc = load(name, tmp_path)
     c, s = build(sc, oracle_library(), g)
     compare(c, g, "prepared_", rtol=2e-6)
+    compare_sort_structures(c, g, "prepared_")
     if "pcisph_k" in g.files:
         assert np.isclose(c.pcisph_k[None], float(g["pcisph_k"]), rtol=2e-6)
     if "rigid_mass" in g.files:
@@ -186,6 +198,7 @@ def test_oracle_matches_reference_sources(name, tmp_path):
         assert counts[:3] == iteration_counts(g, k)[:3], f"step {k + 1}"
         assert abs(counts[3] - iteration_counts(g, k)[3]) <= 1, f"step {k + 1}: CG iterations"
         compare(c, g, f"step{k + 1}_", rtol=2e-5)
+        compare_sort_structures(c, g, f"step{k + 1}_")
         if "rigid_mass" in g.files:
             compare_rigid(c, s, g, k + 1, rtol=2e-5)
 
