@@ -432,6 +432,9 @@ def run_gpu(args, rank, world, local_rank):
                        "mean_iterations": [stats.total_dfsph_iterations / args.steps, stats.total_dfsph_iterations_v / args.steps],
                        "density_error": stats.dfsph_density_error, "divergence_error": stats.dfsph_divergence_error,
                        "early_window": early, "total_particle_steps_per_s": n_total * args.steps / (ms * 1e-3),
+                       # work per step is data dependent (the reference's convergence test averages over fluid AND boundary
+                       # particles, so a scene with relatively fewer boundary particles iterates longer): rate per solver iteration
+                       "fluid_particle_solver_iterations_per_s": n_fluid * (stats.total_dfsph_iterations + stats.total_dfsph_iterations_v) / (ms * 1e-3),
                        "l2": "per-step working set ~0.5 GB > 126 MB L2: no flush needed", "parallelism": f"zslab{world}"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(stats.kernel_launches),
             "clocks": clock_info, "setup_s": time.perf_counter() - t_setup,
