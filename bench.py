@@ -269,6 +269,8 @@ def run_reference(args, rank, world):
         sc = dam_break_scene("dfsph", scale=0.5)
         c, s = make_sim(sc, lib)
         sample = "half-scale geometry (155,800 fluid + 174,750 boundary), early window; the full step exceeded the time box"
+    if world > 1:
+        sample += f"; bounded sample of the {world}-slab weak-scaling workload: one slab (the rate per particle does not depend on the slab count)"
     value, dt, st = time_cpu(s, c, args.steps, max(args.warmup - 2, 0))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
