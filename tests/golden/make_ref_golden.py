@@ -215,7 +215,8 @@ def run_case(name):
         print(f"[{name}] step {s + 1}: {time.time() - t0:.0f} s  " + " ".join(f"{k}={v[-1]}" for k, v in iters.items()), flush=True)
     for k, v in iters.items():
         out["iterations_" + k] = np.array(v, dtype=np.int64)
-    np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), **out)
+    # REF_GOLDEN_OUT redirects the output (sensitivity runs such as TI_SHIM_FMA=1 must not overwrite the fixtures)
+    np.savez_compressed(os.path.join(os.environ.get("REF_GOLDEN_OUT", HERE), f"ref_{name}.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -22,7 +22,21 @@ import inspect
 import itertools
 import textwrap
 
+import os
+
 import numpy as np
+
+# TI_SHIM_FMA=1: accumulate dot products / squared norms with fused multiply-adds, as a fast-math code generator may
+# (sensitivity study of the emulation caveat; the committed fixtures are made WITHOUT it)
+_FMA = os.environ.get("TI_SHIM_FMA") == "1"
+
+
+def _mac(s, a, b):
+    """s + a * b in f32: separately rounded, or fused (exact product in f64, one rounding) under TI_SHIM_FMA."""
+    if _FMA:
+        return np.float32(np.float64(s) + np.float64(a) * np.float64(b))
+    return s + a * b
+
 
 f32 = np.float32
 f64 = np.float64
@@ -252,7 +266,7 @@ class Vector:
     def norm_sqr(self):
         s = self.a[0] * self.a[0]
         for k in range(1, self.a.shape[0]):
-            s = s + self.a[k] * self.a[k]
+            s = _mac(s, self.a[k], self.a[k])
         return _c(s)
 
     def norm(self):
@@ -262,7 +276,7 @@ class Vector:
         b = _arr(o)
         s = self.a[0] * b[0]
         for k in range(1, self.a.shape[0]):
-            s = s + self.a[k] * b[k]
+            s = _mac(s, self.a[k], b[k])
         return _c(s)
 
     def cross(self, o):
