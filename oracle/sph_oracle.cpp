@@ -43,6 +43,11 @@
 #include <string>
 #include <vector>
 
+#include <cstdio>
+#include <cstdlib>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 namespace {
 
 struct V3 {
@@ -1006,8 +1011,31 @@ int sph_abi_version(void) { return SPH_ABI_VERSION; }
 const char* sph_backend_name(void) { return "oracle-cpu"; }
 const char* sph_last_error(const SphHandle* h) { return h ? h->err.c_str() : "null handle"; }
 
+// CPU-baseline fairness on multi-socket hosts: every array is first touched by the creating thread, which would
+// put all particle data on one NUMA node while the OpenMP team spans all of them.  Interleave this process's
+// future pages over the online nodes instead (MPOL_INTERLEAVE; silently skipped where the syscall is filtered,
+// on single-node hosts, or with SPH_ORACLE_NO_INTERLEAVE=1).
+static void interleave_memory_once() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    if (std::getenv("SPH_ORACLE_NO_INTERLEAVE")) return;
+    FILE* f = std::fopen("/sys/devices/system/node/online", "r");
+    if (!f) return;
+    int lo = 0, hi = 0;
+    int n = std::fscanf(f, "%d-%d", &lo, &hi);
+    std::fclose(f);
+    if (n < 2 || hi <= lo || hi >= 1024) return;            // "0" (one node) or an unexpected format
+    unsigned long mask[16] = {0};
+    for (int node = lo; node <= hi; node++) mask[node / (8 * sizeof(unsigned long))] |= 1ul << (node % (8 * sizeof(unsigned long)));
+#ifdef SYS_set_mempolicy
+    (void)syscall(SYS_set_mempolicy, 3 /* MPOL_INTERLEAVE */, mask, (unsigned long)(hi + 2));
+#endif
+}
+
 int sph_create(const SphParams* p, SphHandle** out) {
     if (!p || !out) return SPH_E_INVALID;
+    interleave_memory_once();
     if (p->abi_version != SPH_ABI_VERSION || p->dim != 3 || p->max_particles < 0) return SPH_E_INVALID;
     SphHandle* s = new SphHandle();
     s->P = *p;
