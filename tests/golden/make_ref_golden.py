@@ -107,6 +107,9 @@ CASES = {
     # the solver / viscosity keys are independent (base_solver.py:25,195-200): BASELINE config C4's combination
     "pcisph_implicit": (dict(method="pcisph", viscosity_method="implicit", viscosity=50.0, viscosity_b=20.0, spacing=0.085), 2),
     "wcsph_implicit": (dict(method="wcsph", dt=5e-4, viscosity_method="implicit", viscosity=20.0, viscosity_b=20.0), 2),
+    # BASELINE.json configs[0] ("C1", the reference's own CPU-runnable case): 8,000 fluid + 17,829 box particles at the
+    # shipped resolution (r = 0.01).  ~3 min per step under the emulation; only the prepared and the final state are kept.
+    "c1_wcsph_8k": ("data/scenes/dam_break_8k_wcsph.json", 3, dict(keep_steps=(3,))),
 }
 
 STATE_FIELDS = ("particle_positions", "particle_velocities", "particle_densities", "particle_pressures",
@@ -151,9 +154,16 @@ ITER_RE = {
 
 
 def run_case(name):
-    kw, steps = CASES[name]
-    sc = scene(**kw)
-    method = kw["method"]
+    kw, steps, *rest = CASES[name]
+    opts = rest[0] if rest else {}
+    if isinstance(kw, str):      # a scene file of this repository (same JSON schema as the reference's)
+        with open(os.path.join(os.path.dirname(os.path.dirname(HERE)), kw)) as fh:
+            sc = json.load(fh)
+        sc["Configuration"].update({"exportPly": False, "exportFrame": False})
+        method = sc["Configuration"]["simulationMethod"]
+    else:
+        sc = scene(**kw)
+        method = kw["method"]
     SimConfig, classes = import_reference()
     meshes = sc.get("RigidBodies", []) + sc.get("FluidBodies", [])
     rigid = any(b.get("isDynamic") for b in sc.get("RigidBodies", []))
@@ -205,6 +215,8 @@ def run_case(name):
             iters[k].append(sum(int(m) for m in rx.findall(text)))
         for k, v in snapshot(container, method).items():
             if k in ("particle_object_ids", "particle_is_dynamic", "particle_masses"):
+                continue
+            if "keep_steps" in opts and (s + 1) not in opts["keep_steps"]:
                 continue
             out[f"step{s + 1}_" + k] = v
         if rigid:

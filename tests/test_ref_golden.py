@@ -134,6 +134,8 @@ def canonical(container):
 
 
 def compare(container, g, prefix, rtol, only=None):
+    if prefix + "x0" not in g.files:          # large cases keep only some steps
+        return {}
     perm, x0 = canonical(container)
     n = container.particle_num[None]
     ref_x0 = g[prefix + "x0"]
