@@ -31,6 +31,19 @@ def _lattice(lower_corner, extent, space, dim):
     return grid.reshape(dim, -1).transpose()
 
 
+class _GridCountsView:
+    """Read-only stand-in for the `grid_num_particles` Taichi field (to_numpy / [i])."""
+
+    def __init__(self, engine):
+        self._engine = engine
+
+    def to_numpy(self):
+        return self._engine.get_grid_num_particles()
+
+    def __getitem__(self, i):
+        return self.to_numpy()[i]
+
+
 class BaseContainer:
     # which solver's extra fields the library allocates; subclasses override
     _method = "wcsph"
@@ -438,16 +451,7 @@ class BaseContainer:
     @property
     def grid_num_particles(self):
         """Inclusive scan of per-cell counts in the reference's z-fastest cell order (:132,546)."""
-        class _View:
-            def __init__(self, eng):
-                self._eng = eng
-
-            def to_numpy(self):
-                return self._eng.get_grid_num_particles()
-
-            def __getitem__(self, i):
-                return self.to_numpy()[i]
-        return _View(self._engine)
+        return _GridCountsView(self._engine)
 
     def neighbor_lists(self):
         """CSR (offsets, indices) of N(i) for every particle in current order."""

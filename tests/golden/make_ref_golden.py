@@ -110,6 +110,8 @@ CASES = {
     # BASELINE.json configs[0] ("C1", the reference's own CPU-runnable case): 8,000 fluid + 17,829 box particles at the
     # shipped resolution (r = 0.01).  ~3 min per step under the emulation; only the prepared and the final state are kept.
     "c1_wcsph_8k": ("data/scenes/dam_break_8k_wcsph.json", 3, dict(keep_steps=(3,))),
+    # the same geometry under the north-star method (BASELINE's DFSPH configs use this resolution)
+    "c1_dfsph_8k": ("data/scenes/dam_break_8k_wcsph.json", 2, dict(keep_steps=(2,), override={"simulationMethod": "dfsph", "timeStepSize": 1e-3})),
 }
 
 STATE_FIELDS = ("particle_positions", "particle_velocities", "particle_densities", "particle_pressures",
@@ -160,6 +162,7 @@ def run_case(name):
         with open(os.path.join(os.path.dirname(os.path.dirname(HERE)), kw)) as fh:
             sc = json.load(fh)
         sc["Configuration"].update({"exportPly": False, "exportFrame": False})
+        sc["Configuration"].update(opts.get("override", {}))
         method = sc["Configuration"]["simulationMethod"]
     else:
         sc = scene(**kw)
