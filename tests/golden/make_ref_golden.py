@@ -5,8 +5,10 @@
 Taichi, pybullet and trimesh cannot be installed offline, so the reference (/root/reference/SPH, imported
 in place, never copied) runs on tests/golden/ref_shim: a small emulation of the Taichi API that executes
 the `@ti.kernel` / `@ti.func` bodies as serial Python with f32 numpy scalars (see its docstring for what
-that does and does not reproduce).  The scenes are tiny (a few hundred particles) because every
-floating-point operation is an interpreted numpy call.
+that does and does not reproduce).  Most scenes are tiny (a few hundred particles) because every
+floating-point operation is an interpreted numpy call; BASELINE.json's 8k-particle config C1 runs too, at
+about three (WCSPH) to five (DFSPH) minutes per step.  TI_SHIM_FMA=1 switches the emulation's dot products to
+fused multiply-adds (sensitivity study; write elsewhere with REF_GOLDEN_OUT=<dir>).
 
 Each case writes tests/golden/ref_<case>.npz: the scene (JSON), the state after `prepare()` and after
 every step in a canonical particle order (lexicographic in the insertion position, which both sides keep),
