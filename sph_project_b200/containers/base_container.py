@@ -184,8 +184,8 @@ class BaseContainer:
         self.rigid_body_masses = ObjectTable((), np.float32)
         self.rigid_body_centers_of_mass = ObjectTable((3,), np.float32, self._push_rigid)
         self.rigid_body_rotations = ObjectTable((3, 3), np.float32, self._push_rigid)
-        self.rigid_body_torques = WrenchTable(eng, 1)
         self.rigid_body_forces = WrenchTable(eng, 0)
+        self.rigid_body_torques = WrenchTable(eng, 1, self.rigid_body_forces.state)
         self.rigid_body_velocities = ObjectTable((3,), np.float32, self._push_rigid)
         self.rigid_body_angular_velocities = ObjectTable((3,), np.float32, self._push_rigid)
         self.rigid_body_particle_num = ObjectTable((), np.int32)

@@ -119,16 +119,48 @@ class ObjectTable:
                 self._push(i)
 
 
-class WrenchTable:
-    """rigid_body_forces / rigid_body_torques: accumulated on the device, read here."""
+class _WrenchState:
+    """What the host has taken off the device accumulators.  The library can only zero every object's wrench
+    at once, the reference zeroes one object and one table at a time while it walks its bodies
+    (bullet_solver.py:149-156): a per-object reset moves the device sums into this host-side remainder and clears
+    the one entry there."""
 
-    def __init__(self, engine, which: int):
-        self._engine = engine
+    def __init__(self, engine):
+        self.engine = engine
+        self.remainder = None          # [2][MAX_OBJECTS][3] float32, or None while nothing is held back
+
+    def read(self):
+        dev = np.stack(self.engine.get_rigid_wrench())
+        return dev if self.remainder is None else dev + self.remainder
+
+    def reset(self, which, index):
+        total = self.read()
+        self.engine.zero_rigid_wrench()
+        total[which][index] = 0.0
+        self.remainder = total if np.any(total != 0) else None
+
+    def reset_all(self, which):
+        total = self.read()
+        self.engine.zero_rigid_wrench()
+        total[which] = 0.0
+        self.remainder = total if np.any(total != 0) else None
+
+
+class WrenchTable:
+    """rigid_body_forces / rigid_body_torques: accumulated on the device by the fluid kernels, read and reset here.
+    The two tables of a container share one `_WrenchState`."""
+
+    def __init__(self, engine, which: int, state: "_WrenchState" = None):
+        self._state = state if state is not None else _WrenchState(engine)
         self._which = which
         self.shape = (MAX_OBJECTS,)
 
+    @property
+    def state(self):
+        return self._state
+
     def to_numpy(self):
-        return self._engine.get_rigid_wrench()[self._which]
+        return self._state.read()[self._which]
 
     def __getitem__(self, index):
         return self.to_numpy()[index]
@@ -137,7 +169,9 @@ class WrenchTable:
         # the reference only ever writes zeros here (bullet_solver.py:155-156)
         if np.any(np.asarray(value) != 0):
             raise NotImplementedError("rigid wrench accumulators can only be reset")
-        self._engine.zero_rigid_wrench()
+        self._state.reset(self._which, index)
 
     def fill(self, value):
-        self[0] = value
+        if np.any(np.asarray(value) != 0):
+            raise NotImplementedError("rigid wrench accumulators can only be reset")
+        self._state.reset_all(self._which)

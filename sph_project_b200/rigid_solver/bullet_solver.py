@@ -125,7 +125,8 @@ class PyBulletSolver:
         c = self.container
         forces = c.rigid_body_forces.to_numpy()
         torques = c.rigid_body_torques.to_numpy()
-        c.rigid_body_forces.fill(0.0)   # also clears the torques (one accumulator on the device)
+        c.rigid_body_forces.fill(0.0)
+        c.rigid_body_torques.fill(0.0)
         self._force, self._torque = {}, {}
         for obj in self.bodies:
             self.apply_force(obj, forces[obj])

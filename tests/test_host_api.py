@@ -97,3 +97,38 @@ def test_for_all_neighbors_host_callback(sim):
     assert seen == list(idx[off[i]:off[i + 1]]) and i not in seen
     x = c.particle_positions.to_numpy(c.particle_num[None])
     assert all(np.linalg.norm(x[i] - x[j]) < c.dh + 1e-6 for j in seen)
+
+
+def test_wrench_tables_reset_one_object_and_one_table_at_a_time():
+    """The reference zeroes rigid_body_forces[i] and rigid_body_torques[i] body by body while it walks its bodies
+    (bullet_solver.py:149-156); the library can only clear everything at once."""
+    from sph_project_b200.fields import WrenchTable
+
+    class FakeEngine:
+        def __init__(self):
+            self.f = np.arange(60, dtype=np.float32).reshape(20, 3)
+            self.t = -np.arange(60, dtype=np.float32).reshape(20, 3)
+
+        def get_rigid_wrench(self):
+            return self.f.copy(), self.t.copy()
+
+        def zero_rigid_wrench(self):
+            self.f[:] = 0
+            self.t[:] = 0
+
+    eng = FakeEngine()
+    forces = WrenchTable(eng, 0)
+    torques = WrenchTable(eng, 1, forces.state)
+    f0, t0 = forces.to_numpy().copy(), torques.to_numpy().copy()
+    forces[3] = np.zeros(3)
+    assert np.all(forces[3] == 0) and np.array_equal(forces[4], f0[4]) and np.array_equal(torques[3], t0[3])
+    torques[3] = np.zeros(3)
+    assert np.all(torques[3] == 0) and np.array_equal(torques[5], t0[5])
+    eng.f[4] += 1.0                                   # the kernels keep accumulating on the device
+    assert np.array_equal(forces[4], f0[4] + 1.0)
+    forces.fill(0.0)
+    assert not forces.to_numpy().any() and np.array_equal(torques[5], t0[5])
+    torques.fill(0.0)
+    assert not torques.to_numpy().any() and forces.state.remainder is None
+    with pytest.raises(NotImplementedError):
+        forces[1] = np.ones(3)
