@@ -18,7 +18,7 @@ import numpy as np
 
 from .. import _native as nat
 from .._native import F, S
-from ..fields import HostScalar, ObjectTable, ParticleField, ScalarField, WrenchTable
+from ..fields import HostField, HostScalar, ObjectTable, ParticleField, ScalarField, WrenchTable
 from ..utils import SimConfig
 
 _METHOD_IDS = {"wcsph": nat.METHOD_WCSPH, "pcisph": nat.METHOD_PCISPH, "dfsph": nat.METHOD_DFSPH}
@@ -29,6 +29,13 @@ def _lattice(lower_corner, extent, space, dim):
     axes = [np.arange(lower_corner[i], lower_corner[i] + extent[i], space) for i in range(dim)]
     grid = np.array(np.meshgrid(*axes, sparse=False, indexing="ij"), dtype=np.float32)
     return grid.reshape(dim, -1).transpose()
+
+
+class _NoOpScan:
+    """Stands where upstream keeps `ti.algorithms.PrefixSumExecutor`: the scan is part of the library's sort."""
+
+    def run(self, field):
+        pass
 
 
 class _GridCountsView:
@@ -178,6 +185,7 @@ class BaseContainer:
         self.particle_uids = field(F.UID)  # not upstream: insertion index carried through every sort
 
         self.object_materials = ObjectTable((), np.int32, self._push_object)
+        self.prefix_sum_executor = _NoOpScan()
         self.object_num = HostScalar(num_fluid_object + num_rigid_object + (1 if self.add_domain_box else 0))
         self.rigid_body_is_dynamic = ObjectTable((), np.int32, self._push_object)
         self.rigid_body_original_centers_of_mass = ObjectTable((3,), np.float32, self._push_rigid)
@@ -193,8 +201,8 @@ class BaseContainer:
 
         self.x_vis_buffer = None
         if self.GGUI:
-            self.x_vis_buffer = np.zeros((cap, self.dim), dtype=np.float32)
-            self.color_vis_buffer = np.zeros((cap, 3), dtype=np.float32)
+            self.x_vis_buffer = HostField((cap, self.dim))
+            self.color_vis_buffer = HostField((cap, 3))
 
         if self.add_domain_box:
             box_id = self.object_num[None] - 1  # the last object id goes to the domain box
@@ -356,6 +364,45 @@ class BaseContainer:
 
     def compute_rigid_body_mass(self, object_id: int) -> float:
         return self._engine.compute_rigid_body_mass(object_id)
+
+    def compute_rigid_body_center_of_mass(self, object_id: int):
+        """base_container.py:392-401 (unused by upstream's own solvers): density-weighted mean position of the
+        dynamic particles of one object, computed on the host from the fields."""
+        n = self.particle_num[None]
+        sel = (self.particle_object_ids.to_numpy(n) == object_id) & (self.particle_is_dynamic.to_numpy(n) != 0)
+        w = self.particle_densities.to_numpy(n)[sel].astype(np.float32) * np.float32(self.V0)
+        return (self.particle_positions.to_numpy(n)[sel] * w[:, None]).sum(0) / w.sum()
+
+    def copy_to_numpy(self, np_arr, src_arr):
+        """base_container.py:562-565: the live rows of a field into a caller-owned array."""
+        n = self.particle_num[None]
+        np_arr[:n] = src_arr.to_numpy(n)
+
+    # upstream's neighbourhood search is three calls (base_container.py:544-547); here the whole sort is one library
+    # call, issued by reorder_particles() so that the upstream sequence keeps working unchanged
+    def init_grid(self):
+        pass
+
+    def reorder_particles(self):
+        self._engine.prepare_neighborhood_search()
+
+    # host-side equivalents of upstream's device functions (@ti.func, base_container.py:467-493), for Python-side
+    # tasks over neighbor_lists()
+    def pos_to_index(self, pos):
+        return (np.asarray(pos, dtype=np.float32) / np.float32(self.grid_size)).astype(np.int32)
+
+    def flatten_grid_index(self, grid_index):
+        g = np.asarray(grid_index, dtype=np.int64)
+        return (g[..., 0] * int(self.grid_num[1]) + g[..., 1]) * int(self.grid_num[2]) + g[..., 2]
+
+    def get_flatten_grid_index(self, pos):
+        return self.flatten_grid_index(self.pos_to_index(pos))
+
+    def is_static_rigid_body(self, p):
+        return bool(self.particle_materials[p] == self.material_rigid and not self.particle_is_dynamic[p])
+
+    def is_dynamic_rigid_body(self, p):
+        return bool(self.particle_materials[p] == self.material_rigid and self.particle_is_dynamic[p])
 
     def add_particles(self, object_id, new_particles_num, new_particles_positions, new_particles_velocity,
                       new_particle_density, new_particle_pressure, new_particles_material,

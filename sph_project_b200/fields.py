@@ -90,6 +90,32 @@ class HostScalar:
     def __setitem__(self, index, value):
         self._value = value
 
+    def to_numpy(self):
+        return np.array(self._value)
+
+
+class HostField:
+    """A field that lives on the host only (the GGUI staging buffers): numpy storage behind the field idioms."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self._a = np.zeros(shape, dtype=dtype)
+        self.shape = (self._a.shape[0],)
+
+    def to_numpy(self):
+        return self._a.copy()
+
+    def from_numpy(self, a):
+        self._a[...] = a
+
+    def fill(self, value):
+        self._a[...] = value
+
+    def __getitem__(self, index):
+        return self._a[index]
+
+    def __setitem__(self, index, value):
+        self._a[index] = value
+
 
 class ObjectTable:
     """Per-object table (shape max_num_object) kept on the host and mirrored into the library

@@ -71,6 +71,28 @@ class BaseSolver:
     def compute_pressure_acceleration(self):
         self._run(T.COMPUTE_PRESSURE_ACCELERATION)
 
+    # host-side equivalents of upstream's device functions (@ti.func, base_solver.py:56-103), f32 like the kernels;
+    # for Python-side tasks over container.neighbor_lists() and for tests
+    def kernel_W(self, R_mod):
+        h = np.float32(self.container.dh)
+        k = np.float32(8.0 / np.pi) / (h * h * h)
+        q = np.asarray(R_mod, dtype=np.float32) / h
+        inner = k * (np.float32(6.0) * q * q * q - np.float32(6.0) * q * q + np.float32(1.0))
+        outer = k * np.float32(2.0) * np.power(np.maximum(np.float32(1.0) - q, np.float32(0.0)), np.float32(3.0))
+        return np.where(q <= 0.5, inner, np.where(q <= 1.0, outer, np.float32(0.0))).astype(np.float32)
+
+    def kernel_gradient(self, R):
+        R = np.asarray(R, dtype=np.float32)
+        h = np.float32(self.container.dh)
+        k = np.float32(6.0) * np.float32(8.0 / np.pi) / (h * h * h)
+        r = np.sqrt((R * R).sum(-1, dtype=np.float32))
+        q = r / h
+        safe = np.where(r > 1e-5, r, np.float32(1.0))
+        grad_q = R / (safe * h)[..., None]
+        mag = np.where(q <= 0.5, k * q * (np.float32(3.0) * q - np.float32(2.0)), -k * (np.float32(1.0) - q) ** 2)
+        on = (r > 1e-5) & (q <= 1.0)
+        return np.where(on[..., None], mag[..., None] * grad_q, np.float32(0.0)).astype(np.float32)
+
     def compute_non_pressure_acceleration(self):
         # gravity, surface tension and viscosity (base_solver.py:190-200)
         self.compute_gravity_acceleration()

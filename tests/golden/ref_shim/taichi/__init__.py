@@ -631,6 +631,7 @@ def _lazy(fn, is_kernel):
             return float(out)
         return out
 
+    wrapper.__ti_kind__ = "kernel" if is_kernel else "func"
     return wrapper
 
 

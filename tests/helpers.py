@@ -43,7 +43,7 @@ def scene(method="wcsph", domain_end=(1.0, 1.0, 1.0), block_start=(0.1, 0.1, 0.1
     return {"Configuration": cfg, "FluidBlocks": blocks}
 
 
-def make_sim(scene_dict, lib=None, prepare=True, device=0, slab=None):
+def make_sim(scene_dict, lib=None, prepare=True, device=0, slab=None, GGUI=False):
     """(container, solver) for a scene; lib=None -> the CUDA product, else a bound library."""
     import copy
     from sph_project_b200.containers import DFSPHContainer, PCISPHContainer, WCSPHContainer
@@ -53,7 +53,7 @@ def make_sim(scene_dict, lib=None, prepare=True, device=0, slab=None):
                "dfsph": (DFSPHContainer, DFSPHSolver)}
     config = SimConfig(config=copy.deepcopy(scene_dict), verbose=False)
     C, S = classes[config.get_cfg("simulationMethod")]
-    container = C(config, GGUI=False, engine_library=lib, device=device, slab=slab)
+    container = C(config, GGUI=GGUI, engine_library=lib, device=device, slab=slab)
     solver = S(container)
     if prepare:
         solver.prepare()
