@@ -129,3 +129,29 @@ def test_halo_ranges_are_contiguous_and_aligned():
     for order, layer in ((order0, z_cut - 1), (order0, z_cut), (order1, z_cut), (order1, z_cut - 1)):
         idx = np.nonzero(cell[order, 2] == layer)[0]
         assert idx.size and idx[-1] - idx[0] + 1 == idx.size
+
+
+def test_balanced_ranges_properties():
+    """Property test (hypothesis): for any layer histogram the slabs are contiguous, cover every layer exactly once,
+    respect the minimum thickness, and no slab is heavier than the ideal share by more than its two heaviest
+    boundary layers (the cut can only move by whole layers)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.integers(1, 8).flatmap(lambda w: st.tuples(st.just(w), st.lists(st.integers(0, 50_000), min_size=2 * w, max_size=96))))
+    def check(case):
+        world, counts = case
+        ranges = balanced_ranges(counts, world)
+        assert ranges[0][0] == 0 and ranges[-1][1] == len(counts)
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        assert all(hi - lo >= 2 for lo, hi in ranges)
+        total = sum(counts)
+        heaviest = max(counts) if counts else 0
+        # the min-thickness clamp may force weight onto a slab when the histogram is concentrated in few layers;
+        # otherwise each slab stays within two layers' worth of the ideal share
+        if all(hi - lo > 2 for lo, hi in ranges):
+            for lo, hi in ranges:
+                assert sum(counts[lo:hi]) <= total / world + 2 * heaviest
+
+    check()
