@@ -6,7 +6,7 @@
 // Instead tests/golden/make_ref_golden.py imports /root/reference/SPH in place and steps it on
 // tests/golden/ref_shim, a small emulation of the Taichi API (kernel bodies executed as serial Python
 // on f32 numpy scalars).  The committed fixtures tests/golden/ref_*.npz hold its state after prepare()
-// and after every step for thirteen tiny WCSPH / PCISPH / DFSPH scenes and BASELINE config C1 (domain box, over-dense blocks that
+// and after every step for fifteen tiny WCSPH / PCISPH / DFSPH scenes and BASELINE config C1 (domain box, over-dense blocks that
 // make the pressure solvers iterate, implicit viscosity, emitter, late-entry block, mesh bodies, a dynamic
 // rigid cube coupled to each solver); tests/test_ref_golden.py checks this
 // file against them: insertion lattice and integer fields bit for bit, every float field within 2e-5

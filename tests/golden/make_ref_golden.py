@@ -31,7 +31,7 @@ REFERENCE = "/root/reference"
 
 
 def scene(method, dt=1e-3, viscosity_method="standard", spacing=0.09, velocity=(0.0, -1.0, 0.0), g_upper=None,
-          block_end=(0.8, 0.85, 0.8), viscosity=0.05, viscosity_b=0.02, add_box=True, domain_end=1.6, rigid=False, late_block=False, mesh_bodies=False):
+          block_end=(0.8, 0.85, 0.8), viscosity=0.05, viscosity_b=0.02, add_box=True, domain_end=1.6, rigid=False, late_block=False, mesh_bodies=False, second_block_density=None):
     cfg = {"domainStart": [0.0, 0.0, 0.0], "domainEnd": [domain_end] * 3, "particleRadius": 0.05,
            "particleSpacing": spacing, "addDomainBox": add_box, "density0": 1000, "gravitation": [0.0, -9.81, 0.0],
            "simulationMethod": method, "viscosityMethod": viscosity_method, "timeStepSize": dt,
@@ -45,6 +45,12 @@ def scene(method, dt=1e-3, viscosity_method="standard", spacing=0.09, velocity=(
         out["FluidBlocks"].append({"objectId": 1, "start": [0.9, 0.5, 0.9], "end": [1.2, 0.8, 1.2], "translation": [0.0, 0.0, 0.0],
                                    "scale": [1, 1, 1], "velocity": [0.0, -2.0, 0.0], "density": 1000.0, "color": [200, 50, 50],
                                    "entryTime": 0.0008})
+    if second_block_density is not None:
+        # a lighter block next to the first from the start: particle masses (V0 x density, base_container.py:411) differ
+        # between neighbours in the pressure / viscosity / surface-tension sums
+        out["FluidBlocks"].append({"objectId": 1, "start": [0.82, 0.3, 0.35], "end": [1.1, 0.7, 0.8], "translation": [0.0, 0.0, 0.0],
+                                   "scale": [1, 1, 1], "velocity": [-1.0, 0.0, 0.0], "density": second_block_density,
+                                   "color": [200, 50, 50], "entryTime": -1.0})
     if mesh_bodies:
         # a static, rotated rigid cube next to the block and a fluid body cut from a mesh (base_container.py:611-717)
         out["RigidBodies"] = [{"objectId": 1, "geometryFile": "cube.obj", "translation": [1.05, 0.45, 0.6],
@@ -109,6 +115,8 @@ CASES = {
     # the solver / viscosity keys are independent (base_solver.py:25,195-200): BASELINE config C4's combination
     "pcisph_implicit": (dict(method="pcisph", viscosity_method="implicit", viscosity=50.0, viscosity_b=20.0, spacing=0.085), 2),
     "wcsph_implicit": (dict(method="wcsph", dt=5e-4, viscosity_method="implicit", viscosity=20.0, viscosity_b=20.0), 2),
+    "wcsph_two_densities": (dict(method="wcsph", dt=5e-4, second_block_density=600.0), 3),
+    "dfsph_two_densities": (dict(method="dfsph", second_block_density=600.0), 2),
     # BASELINE.json configs[0] ("C1", the reference's own CPU-runnable case): 8,000 fluid + 17,829 box particles at the
     # shipped resolution (r = 0.01).  ~3 min per step under the emulation; only the prepared and the final state are kept.
     "c1_wcsph_8k": ("data/scenes/dam_break_8k_wcsph.json", 3, dict(keep_steps=(3,))),
