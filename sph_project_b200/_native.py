@@ -202,11 +202,17 @@ def load_cuda_library() -> C.CDLL:
     """Load the sm_100a CUDA library.  No fallback: a missing build is an error."""
     global _cuda_lib
     if _cuda_lib is None:
-        if not os.path.exists(CUDA_LIBRARY_PATH):
+        # SPH_B200_LIBRARY selects another build of the SAME CUDA library (a tuning variant from `make variants`);
+        # it is still sm_100a-only and must report the CUDA backend
+        path = os.environ.get("SPH_B200_LIBRARY") or CUDA_LIBRARY_PATH
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{CUDA_LIBRARY_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(or `make -C sph_project_b200/csrc`).  sph_project_b200 has no CPU fallback.")
-        _cuda_lib = bind(C.CDLL(CUDA_LIBRARY_PATH))
+        lib = bind(C.CDLL(path))
+        if lib.sph_backend_name().decode() != "cuda-sm100a":
+            raise RuntimeError(f"{path} is not the sm_100a CUDA library (backend {lib.sph_backend_name().decode()!r})")
+        _cuda_lib = lib
     return _cuda_lib
 
 

@@ -25,6 +25,16 @@ namespace {
 
 extern __shared__ __align__(16) float4 dyn_smem[];
 
+// Compile-time tuning knobs for variant builds (`make variants`, tools/tune_variants.sh).  Undefined, the
+// preprocessed source -- and therefore the shipped binary -- is exactly what was validated on hardware.
+//   SPH_CORRECT_MINB   min resident CTAs per SM for k_dfsph_correct (caps its registers: 56 -> 48 / 40)
+//   SPH_LIST_UNROLL8   eight index -> record gather chains in flight in rec_neighbors instead of four
+#ifdef SPH_CORRECT_MINB
+#define SPH_CORRECT_BOUNDS __launch_bounds__(SPH_BLOCK, SPH_CORRECT_MINB)
+#else
+#define SPH_CORRECT_BOUNDS __launch_bounds__(SPH_BLOCK)
+#endif
+
 // rigid_body_forces / rigid_body_torques accumulation (base_solver.py:174-187 and twins)
 __device__ __forceinline__ void add_wrench(const Dev& d, int obj, float3 force, float3 at) {
     if (obj < 0 || obj >= SPH_MAX_OBJECTS) return;
@@ -47,6 +57,21 @@ __device__ __forceinline__ void rec_neighbors(const Consts& c, const Dev& d, con
             const int* __restrict__ col = d.nbr + i;
             const size_t stride = (size_t)d.nbr_stride;
             int k = 0;
+#ifdef SPH_LIST_UNROLL8
+            for (; k + 8 <= n; k += 8) {
+                int j[8];
+                float4 p[8], hh[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) j[u] = __ldg(col + (size_t)(k + u) * stride);
+#pragma unroll
+                for (int u = 0; u < 8; u++) ldg_rec(rec + j[u], p[u], hh[u]);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float3 R = make_float3(pi.x - p[u].x, pi.y - p[u].y, pi.z - p[u].z);
+                    visit(j[u], p[u], hh[u], R, dist2(R));
+                }
+            }
+#endif
             for (; k + 4 <= n; k += 4) {
                 const int j0 = __ldg(col + (size_t)k * stride), j1 = __ldg(col + (size_t)(k + 1) * stride);
                 const int j2 = __ldg(col + (size_t)(k + 2) * stride), j3 = __ldg(col + (size_t)(k + 3) * stride);
@@ -330,7 +355,7 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, De
 // DFSPH correct_divergence_step (DFSPH.py:161-202) / correct_density_error_step (:245-283).
 // recB.hi = (kappa_j, kappa_j / rho_j, rho_j, m_j); the new velocity goes to vm and to recA.hi
 template <bool LIST>
-__global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_correct(Consts c, Dev d) {
+__global__ void SPH_CORRECT_BOUNDS k_dfsph_correct(Consts c, Dev d) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
