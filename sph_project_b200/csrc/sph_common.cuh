@@ -17,7 +17,9 @@
 
 #include "../../include/sph_b200.h"
 
+#ifndef SPH_BLOCK   // variant builds may override it (Makefile `variants`); every kernel and chunk size follows
 #define SPH_BLOCK 128
+#endif
 
 struct Consts {
     int N;            // particle_num
