@@ -106,10 +106,27 @@ struct Dev {
 
 // one 256-bit read-only gather of a neighbour record
 __device__ __forceinline__ void ldg_rec(const Rec* p, float4& lo, float4& hi) {
+#ifdef SPH_REC_EVICT_LAST   // variant build: ask the L1 to keep gathered records (they are re-read by neighbouring lanes / warps)
+    asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
         : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
         : "l"(p));
 }
+
+// neighbour-list index load (streamed once per sweep).  Variant build SPH_IDX_NO_ALLOCATE keeps it out of the L1 so
+// that the lines stay available to the record gathers.
+#ifdef SPH_IDX_NO_ALLOCATE
+__device__ __forceinline__ int ldg_idx_no_allocate(const int* p) {
+    int v;
+    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+#define SPH_LDG_IDX(ptr) ldg_idx_no_allocate(ptr)
+#else
+#define SPH_LDG_IDX(ptr) __ldg(ptr)
+#endif
 
 // ---- small vector helpers -------------------------------------------------------------------
 __device__ __forceinline__ float3 f3(float4 a) { return make_float3(a.x, a.y, a.z); }

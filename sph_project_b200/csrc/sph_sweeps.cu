@@ -29,6 +29,7 @@ extern __shared__ __align__(16) float4 dyn_smem[];
 // preprocessed source -- and therefore the shipped binary -- is exactly what was validated on hardware.
 //   SPH_CORRECT_MINB   min resident CTAs per SM for k_dfsph_correct (caps its registers: 56 -> 48 / 40)
 //   SPH_LIST_UNROLL8   eight index -> record gather chains in flight in rec_neighbors instead of four
+//   SPH_IDX_NO_ALLOCATE / SPH_REC_EVICT_LAST   L1 allocation hints for the list stream / the record gathers (sph_common.cuh)
 #ifdef SPH_CORRECT_MINB
 #define SPH_CORRECT_BOUNDS __launch_bounds__(SPH_BLOCK, SPH_CORRECT_MINB)
 #else
@@ -62,7 +63,7 @@ __device__ __forceinline__ void rec_neighbors(const Consts& c, const Dev& d, con
                 int j[8];
                 float4 p[8], hh[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) j[u] = __ldg(col + (size_t)(k + u) * stride);
+                for (int u = 0; u < 8; u++) j[u] = SPH_LDG_IDX(col + (size_t)(k + u) * stride);
 #pragma unroll
                 for (int u = 0; u < 8; u++) ldg_rec(rec + j[u], p[u], hh[u]);
 #pragma unroll
@@ -73,8 +74,8 @@ __device__ __forceinline__ void rec_neighbors(const Consts& c, const Dev& d, con
             }
 #endif
             for (; k + 4 <= n; k += 4) {
-                const int j0 = __ldg(col + (size_t)k * stride), j1 = __ldg(col + (size_t)(k + 1) * stride);
-                const int j2 = __ldg(col + (size_t)(k + 2) * stride), j3 = __ldg(col + (size_t)(k + 3) * stride);
+                const int j0 = SPH_LDG_IDX(col + (size_t)k * stride), j1 = SPH_LDG_IDX(col + (size_t)(k + 1) * stride);
+                const int j2 = SPH_LDG_IDX(col + (size_t)(k + 2) * stride), j3 = SPH_LDG_IDX(col + (size_t)(k + 3) * stride);
                 float4 p0, h0, p1, h1, p2, h2, p3, h3;
                 ldg_rec(rec + j0, p0, h0); ldg_rec(rec + j1, p1, h1); ldg_rec(rec + j2, p2, h2); ldg_rec(rec + j3, p3, h3);
                 float3 R;
@@ -84,7 +85,7 @@ __device__ __forceinline__ void rec_neighbors(const Consts& c, const Dev& d, con
                 R = make_float3(pi.x - p3.x, pi.y - p3.y, pi.z - p3.z); visit(j3, p3, h3, R, dist2(R));
             }
             for (; k < n; k++) {
-                const int j = __ldg(col + (size_t)k * stride);
+                const int j = SPH_LDG_IDX(col + (size_t)k * stride);
                 float4 pj, hj;
                 ldg_rec(rec + j, pj, hj);
                 const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
