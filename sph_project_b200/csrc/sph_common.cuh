@@ -106,7 +106,11 @@ struct Dev {
 
 // one 256-bit read-only gather of a neighbour record
 __device__ __forceinline__ void ldg_rec(const Rec* p, float4& lo, float4& hi) {
-#ifdef SPH_REC_EVICT_LAST   // variant build: ask the L1 to keep gathered records (they are re-read by neighbouring lanes / warps)
+#if defined(SPH_REC_L2_EVICT_LAST) && defined(SPH_REC_EVICT_LAST)   // variant builds: cache-residency hints for the records,
+    asm("ld.global.nc.L1::evict_last.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"   // which neighbouring lanes / warps re-read
+#elif defined(SPH_REC_L2_EVICT_LAST)   // (the L2 hint exists for 256-bit loads only; the 4-byte list stream cannot carry one)
+    asm("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#elif defined(SPH_REC_EVICT_LAST)
     asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 #else
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
