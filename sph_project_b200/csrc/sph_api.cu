@@ -176,6 +176,33 @@ int dfsph_correct_density_error(SphHandle* h, int* iters, float* err) {
     int it = 0, rc;
     float e = 0.f;
     sph_launch_dfsph_density_star(h, true);
+#ifdef SPH_DEVICE_CONVERGENCE
+    // Variant build: launch `batch` iterations back to back; each ends with the loop-exit test on the device, after
+    // which the remaining launches of the batch return at once.  One host read per batch instead of one per iteration;
+    // the iteration at which the solve stops is the same as in the host loop below.
+    {
+        static const int batch = [] { const char* v = std::getenv("SPH_B200_BATCH_ITERS"); int b = v ? std::atoi(v) : 4; return b < 1 ? 1 : (b > 64 ? 64 : b); }();
+        double ctrl[CTRL_COUNT] = {0.0, 0.0, 0.0};
+        if ((rc = zero_red(h, RED_ERR))) return rc;
+        if ((rc = zero_red(h, CTRL_DONE, CTRL_COUNT))) return rc;
+        while (it < 1000) {
+            for (int b = 0; b < batch && it + b < 1000; b++) {
+                sph_launch_dfsph_correct_density(h, true);
+                sph_launch_dfsph_density_star(h, true);
+                if ((rc = sph_slab_allreduce_red(h, RED_ERR, 1))) return rc;
+                sph_launch_dfsph_solve_check(h, global_particle_num(h), 0.0001f);
+            }
+            CUDA_TRY(h, cudaMemcpyAsync(ctrl, h->d.red + CTRL_DONE, sizeof(ctrl), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            it = (int)ctrl[CTRL_ITERS - CTRL_DONE];
+            e = (float)ctrl[CTRL_ERR - CTRL_DONE];
+            if (ctrl[0] != 0.0) break;
+        }
+        if ((rc = zero_red(h, CTRL_DONE, CTRL_COUNT))) return rc;   // the same kernels serve the divergence solve and the task API
+        *iters = it; *err = e;
+        return last_launch(h);
+    }
+#endif
     while (it < 1 || it < 1000) {
         sph_launch_dfsph_correct_density(h, true);
         if ((rc = zero_red(h, RED_ERR))) return rc;

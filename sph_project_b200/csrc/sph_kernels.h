@@ -14,6 +14,13 @@ enum RedSlot {
     RED_COUNT = 16
 };
 
+#ifdef SPH_DEVICE_CONVERGENCE
+// Variant build: the DFSPH density solve tests convergence on the device, so the host reads the result
+// once per batch of iterations instead of once per iteration.  Control words live in spare slots of Dev::red.
+enum SolveCtrlSlot { CTRL_DONE = 32, CTRL_ITERS = 33, CTRL_ERR = 34, CTRL_COUNT = 3 };
+void sph_launch_dfsph_solve_check(SphHandle* h, float n_global, float eta);
+#endif
+
 #ifdef __CUDACC__
 // sum `v` over the block, one atomicAdd(double) per block
 __device__ __forceinline__ void block_reduce_add(double* dst, double v) {

@@ -30,6 +30,7 @@ extern __shared__ __align__(16) float4 dyn_smem[];
 //   SPH_CORRECT_MINB   min resident CTAs per SM for k_dfsph_correct (caps its registers: 56 -> 48 / 40)
 //   SPH_LIST_UNROLL8   eight index -> record gather chains in flight in rec_neighbors instead of four
 //   SPH_IDX_NO_ALLOCATE / SPH_REC_EVICT_LAST   L1 allocation hints for the list stream / the record gathers (sph_common.cuh)
+//   SPH_DEVICE_CONVERGENCE   loop-exit test of the DFSPH density solve on the device, host reads once per batch (sph_api.cu)
 #ifdef SPH_CORRECT_MINB
 #define SPH_CORRECT_BOUNDS __launch_bounds__(SPH_BLOCK, SPH_CORRECT_MINB)
 #else
@@ -320,6 +321,9 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_alpha(Consts c, Dev d) {
 // error sum (compute_density_derivative_error :205-211 / compute_density_error :285-294).
 template <bool STAR, bool LIST, bool FUSED>
 __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, Dev d) {
+#ifdef SPH_DEVICE_CONVERGENCE
+    if (d.red[CTRL_DONE] != 0.0) return;   // uniform over the grid: no thread reaches the block reduction
+#endif
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     float err = 0.0f;
     if (SPH_IS_ROW(c, i)) {
@@ -357,6 +361,9 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_dfsph_density_change(Consts c, De
 // recB.hi = (kappa_j, kappa_j / rho_j, rho_j, m_j); the new velocity goes to vm and to recA.hi
 template <bool LIST>
 __global__ void SPH_CORRECT_BOUNDS k_dfsph_correct(Consts c, Dev d) {
+#ifdef SPH_DEVICE_CONVERGENCE
+    if (d.red[CTRL_DONE] != 0.0) return;   // the solve converged earlier in this batch: a speculative launch does nothing
+#endif
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     SPH_ROW_OR_RETURN(c, i);
     const float4 pi = d.pv[i];
@@ -386,6 +393,21 @@ __global__ void SPH_CORRECT_BOUNDS k_dfsph_correct(Consts c, Dev d) {
     d.vm[i] = v;
     d.recA[i].hi = v;
 }
+
+#ifdef SPH_DEVICE_CONVERGENCE
+// The loop-exit test of DFSPH.correct_density_error (DFSPH.py:236-242) on the device, with the host's arithmetic
+// (f32 division of the f64 sum by the particle count, compare with eta); also clears the error slot for the next
+// iteration (the host path does that with a memset).
+__global__ void k_dfsph_solve_check(Dev d, float n_global, float eta) {
+    if (d.red[CTRL_DONE] == 0.0) {
+        const float e = (float)d.red[RED_ERR] / n_global;
+        d.red[CTRL_ITERS] += 1.0;
+        d.red[CTRL_ERR] = (double)e;
+        if (e <= eta) d.red[CTRL_DONE] = 1.0;
+    }
+    d.red[RED_ERR] = 0.0;
+}
+#endif
 
 // PCISPH compute_density_star (PCISPH.py:32-62): predicted positions, no self term, neighbour
 // set from the current positions.  Accumulates sum max(0, rho*/rho0 - 1) into red[RED_ERR].
@@ -642,6 +664,13 @@ void sph_launch_dfsph_correct_density(SphHandle* h, bool aux_ready) {
     LAUNCH_LIST(k_dfsph_correct, );
     sph_ghost_dirty(h, GHOST_VEL);
 }
+#ifdef SPH_DEVICE_CONVERGENCE
+void sph_launch_dfsph_solve_check(SphHandle* h, float n_global, float eta) {
+    SphProf _prof(h, "k_dfsph_solve_check");
+    k_dfsph_solve_check<<<1, 1, 0, h->stream>>>(h->d, n_global, eta);
+    h->launches++;
+}
+#endif
 void sph_launch_pcisph_density_star(SphHandle* h) { LAUNCH_LIST(k_pcisph_density_star, ); }
 void sph_launch_cg_prepare1(SphHandle* h) { ensure_records(h, true); LAUNCH_LIST(k_cg_prepare1, ); }
 void sph_launch_cg_Ap(SphHandle* h, bool aux_ready) {   // recB.hi = (., ., rho, m): unchanged inside the CG loop
