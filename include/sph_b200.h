@@ -137,7 +137,11 @@ typedef enum SphScalar {
     SPH_S_VISCOSITY = 9,
     SPH_S_VISCOSITY_B = 10,
     SPH_S_NUM_CELLS = 11,
-    SPH_S_MAX_PARTICLES = 12
+    SPH_S_MAX_PARTICLES = 12,
+    /* diagnostics of the brick-tile sweeps (no reference counterpart; the oracle reports 0) */
+    SPH_S_ACTIVE_BRICKS = 13,     /* bricks that own fluid rows as of the last sort */
+    SPH_S_MAX_WINDOW_SLOTS = 14,  /* largest brick window (particles) seen since the last sort */
+    SPH_S_WINDOW_OVERFLOWS = 15   /* brick windows above the shared-memory budget since the last sort */
 } SphScalar;
 
 /* One id per upstream @ti.kernel on the hot path.  sph_run_task launches

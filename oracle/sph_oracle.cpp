@@ -1160,6 +1160,7 @@ int sph_get_scalar(SphHandle* h, int32_t s, double* out) {
         case SPH_S_VISCOSITY_B: *out = h->P.viscosity_b; break;
         case SPH_S_NUM_CELLS: *out = h->ncell; break;
         case SPH_S_MAX_PARTICLES: *out = h->cap; break;
+        case SPH_S_ACTIVE_BRICKS: case SPH_S_MAX_WINDOW_SLOTS: case SPH_S_WINDOW_OVERFLOWS: *out = 0; break;   // CUDA-path diagnostics
         default: return fail(h, SPH_E_INVALID, "unknown scalar");
     }
     return SPH_OK;

@@ -89,6 +89,7 @@ class S:
     """SphScalar ids."""
     DT, PARTICLE_NUM, FLUID_PARTICLE_NUM, PCISPH_K, DENSITY_ERROR, CG_ALPHA, CG_BETA, CG_ERROR = range(8)
     G_UPPER, VISCOSITY, VISCOSITY_B, NUM_CELLS, MAX_PARTICLES = range(8, 13)
+    ACTIVE_BRICKS, MAX_WINDOW_SLOTS, WINDOW_OVERFLOWS = 13, 14, 15   # diagnostics of the brick-tile sweeps
 
 
 class T:

@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "sph_kernels.h"
+#include "sph_brick.cuh"
 
 namespace {
 
@@ -26,6 +27,12 @@ int check_cuda(SphHandle* h, cudaError_t e, const char* what) {
     do {                                                  \
         int _rc = check_cuda((h), (expr), #expr);         \
         if (_rc) return _rc;                              \
+    } while (0)
+
+// every ABI entry runs on the handle's device whatever the caller's current device is
+#define ON_DEVICE(h)                                                                             \
+    do {                                                                                         \
+        if (cudaSetDevice((h)->P.device) != cudaSuccess) return check_cuda((h), cudaGetLastError(), "cudaSetDevice"); \
     } while (0)
 
 int last_launch(SphHandle* h) {
@@ -82,6 +89,7 @@ void refresh_consts(SphHandle* h) {
     c.kG_inv_h = (float)(6.0 * k / P.dh);
     c.V0 = (float)P.V0; c.rho0 = (float)P.density0; c.inv_rho0 = 1.0f / c.rho0;
     c.dt = (float)P.dt; c.inv_dt = 1.0f / c.dt;
+    c.corr_thresh = 1e-5f * c.dt;
     c.g_upper = (float)P.g_upper;
     c.gx = (float)P.gravity[0]; c.gy = (float)P.gravity[1]; c.gz = (float)P.gravity[2];
     c.visc_cf = (float)(2.0 * (3 + 2) * P.viscosity);
@@ -112,6 +120,7 @@ int zero_red(SphHandle* h, int slot, int count = 1) {
 
 int update_dynamic_rigid_flag(SphHandle* h) {
     if (!h->dyn_rigid_dirty) return SPH_OK;
+    if (sph_is_slab(h)) return SPH_OK;   // Z-slabs: the flag is global, summed over the ranks by the next sort (sph_slab.cu)
     int* flag = h->d.scan_tmp;   // any int scratch
     CUDA_TRY(h, cudaMemsetAsync(flag, 0, sizeof(int), h->stream));
     sph_launch_count_dynamic_rigid(h, flag);
@@ -147,75 +156,70 @@ float pcisph_k_host(const SphHandle* h) {
 }
 
 // ---- solver loops ---------------------------------------------------------------------------
-// DFSPH.correct_divergence_error (DFSPH.py:139-159)
-int dfsph_correct_divergence_error(SphHandle* h, int* iters, float* err) {
+// DFSPH.correct_divergence_error (DFSPH.py:139-159) / correct_density_error (:225-243).
+// Density change, the kappa of the next correction step and the error sum are one fused kernel (same arithmetic as the
+// three upstream kernels; sph_run_task exposes them separately).  The loop-exit test runs on the device, in the last
+// CTA of every density-change launch; the host launches a batch of iterations back to back — as many as the previous
+// solve of this kind needed — and reads the outcome once per batch.  Launches after convergence return at once, so the
+// solve stops at the same iteration as the reference's host-driven loop.
+int dfsph_solve(SphHandle* h, bool density, int* iters, float* err) {
     const Consts& c = h->c;
-    int it = 0, rc;
+    const float eta = density ? 0.0001f : 0.001f * c.rho0 / c.dt;
+    int rc;
+    auto density_change = [&](int mode, bool spec) {
+        if (density) sph_launch_dfsph_density_star(h, true, mode, spec, eta);
+        else sph_launch_dfsph_density_derivative(h, true, mode, spec, eta);
+    };
+    auto correct = [&](bool spec) {
+        if (density) sph_launch_dfsph_correct_density(h, true, spec);
+        else sph_launch_dfsph_correct_divergence(h, true, spec);
+    };
+    int it = 0;
     float e = 0.f;
-    // density derivative, kappa_v and the error sum are one fused kernel here (same arithmetic as
-    // the three upstream kernels; sph_run_task exposes them separately)
-    sph_launch_dfsph_density_derivative(h, true);
-    while (it < 1 || it < 1000) {
-        sph_launch_dfsph_correct_divergence(h, true);
-        if ((rc = zero_red(h, RED_ERR))) return rc;
-        sph_launch_dfsph_density_derivative(h, true);
-        if ((rc = sph_slab_allreduce_red(h, RED_ERR, 1))) return rc;
-        if ((rc = read_red(h))) return rc;   // the reference's per-iteration device->host read
-        e = (float)h->h_red[RED_ERR] / global_particle_num(h);
-        const float eta = 0.001f * c.rho0 / c.dt;
-        it++;
-        if (e <= eta) break;
-    }
-    *iters = it; *err = e;
-    return last_launch(h);
-}
-
-// DFSPH.correct_density_error (DFSPH.py:225-243)
-int dfsph_correct_density_error(SphHandle* h, int* iters, float* err) {
-    const Consts& c = h->c;
-    int it = 0, rc;
-    float e = 0.f;
-    sph_launch_dfsph_density_star(h, true);
-#ifdef SPH_DEVICE_CONVERGENCE
-    // Variant build: launch `batch` iterations back to back; each ends with the loop-exit test on the device, after
-    // which the remaining launches of the batch return at once.  One host read per batch instead of one per iteration;
-    // the iteration at which the solve stops is the same as in the host loop below.
-    {
-        static const int batch = [] { const char* v = std::getenv("SPH_B200_BATCH_ITERS"); int b = v ? std::atoi(v) : 4; return b < 1 ? 1 : (b > 64 ? 64 : b); }();
-        double ctrl[CTRL_COUNT] = {0.0, 0.0, 0.0};
-        if ((rc = zero_red(h, RED_ERR))) return rc;
-        if ((rc = zero_red(h, CTRL_DONE, CTRL_COUNT))) return rc;
-        while (it < 1000) {
-            for (int b = 0; b < batch && it + b < 1000; b++) {
-                sph_launch_dfsph_correct_density(h, true);
-                sph_launch_dfsph_density_star(h, true);
-                if ((rc = sph_slab_allreduce_red(h, RED_ERR, 1))) return rc;
-                sph_launch_dfsph_solve_check(h, global_particle_num(h), 0.0001f);
-            }
-            CUDA_TRY(h, cudaMemcpyAsync(ctrl, h->d.red + CTRL_DONE, sizeof(ctrl), cudaMemcpyDeviceToHost, h->stream));
-            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-            it = (int)ctrl[CTRL_ITERS - CTRL_DONE];
-            e = (float)ctrl[CTRL_ERR - CTRL_DONE];
-            if (ctrl[0] != 0.0) break;
+    if (sph_is_slab(h)) {
+        // Z-slabs: the error sum crosses ranks (ncclAllReduce), so the test stays on the host, once per iteration
+        density_change(0, false);
+        while (it < 1 || it < 1000) {
+            correct(false);
+            if ((rc = zero_red(h, RED_ERR))) return rc;
+            density_change(1, false);
+            if ((rc = sph_slab_allreduce_red(h, RED_ERR, 1))) return rc;
+            if ((rc = read_red(h))) return rc;   // the reference's per-iteration device->host read
+            e = (float)h->h_red[RED_ERR] / global_particle_num(h);
+            it++;
+            if (e <= eta) break;
         }
-        if ((rc = zero_red(h, CTRL_DONE, CTRL_COUNT))) return rc;   // the same kernels serve the divergence solve and the task API
         *iters = it; *err = e;
         return last_launch(h);
     }
-#endif
-    while (it < 1 || it < 1000) {
-        sph_launch_dfsph_correct_density(h, true);
-        if ((rc = zero_red(h, RED_ERR))) return rc;
-        sph_launch_dfsph_density_star(h, true);
-        if ((rc = sph_slab_allreduce_red(h, RED_ERR, 1))) return rc;
-        if ((rc = read_red(h))) return rc;
-        e = (float)h->h_red[RED_ERR] / global_particle_num(h);
-        it++;
-        if (e <= 0.0001f) break;
+    if ((rc = zero_red(h, RED_ERR))) return rc;
+    if ((rc = zero_red(h, CTRL_DONE, CTRL_COUNT))) return rc;
+    density_change(0, false);
+    int& hint = h->solve_hint[density ? 0 : 1];
+    int launched = 0;
+    double ctrl[CTRL_COUNT] = {0.0, 0.0, 0.0};
+    while (launched < 1000) {
+        int batch = launched == 0 ? (hint < 1 ? 1 : hint) : (hint / 8 < 2 ? 2 : hint / 8);
+        if (h->solve_batch > 0) batch = h->solve_batch;   // SPH_B200_BATCH_ITERS: fixed batch size (1 = a host read per iteration)
+        if (batch > 1000 - launched) batch = 1000 - launched;
+        for (int b = 0; b < batch; b++) {
+            correct(true);
+            density_change(2, true);
+        }
+        launched += batch;
+        CUDA_TRY(h, cudaMemcpyAsync(h->h_red + CTRL_DONE, h->d.red + CTRL_DONE, sizeof(double) * CTRL_COUNT, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (int k = 0; k < CTRL_COUNT; k++) ctrl[k] = h->h_red[CTRL_DONE + k];
+        if (ctrl[0] != 0.0) break;
     }
+    it = (int)ctrl[CTRL_ITERS - CTRL_DONE];
+    e = (float)ctrl[CTRL_ERR - CTRL_DONE];
+    hint = it;
     *iters = it; *err = e;
     return last_launch(h);
 }
+int dfsph_correct_divergence_error(SphHandle* h, int* iters, float* err) { return dfsph_solve(h, false, iters, err); }
+int dfsph_correct_density_error(SphHandle* h, int* iters, float* err) { return dfsph_solve(h, true, iters, err); }
 
 int pcisph_density_star(SphHandle* h) {
     int rc;
@@ -281,7 +285,7 @@ int implicit_viscosity_solve(SphHandle* h, int* iters, float* err) {
         it++;
     }
     sph_launch_cg_velocity_from_x(h);
-    sph_launch_viscosity(h, true);
+    sph_launch_viscosity(h);
     sph_launch_cg_velocity_restore(h);
     sph_launch_cg_prepare_guess(h);
     *iters = it; *err = tol;
@@ -293,7 +297,7 @@ int non_pressure_acceleration(SphHandle* h, SphStepStats* st) {
     sph_launch_gravity(h);
     sph_launch_surface_tension(h);
     if (h->P.visc_method == SPH_VISC_STANDARD) {
-        sph_launch_viscosity(h, true);   // surface tension just prepared aux
+        sph_launch_viscosity(h);
     } else {
         int it; float e;
         int rc = implicit_viscosity_solve(h, &it, &e);
@@ -341,8 +345,7 @@ int step_once(SphHandle* h, SphStepStats* st) {
             if (h->c.has_dynamic_rigid) sph_launch_renew_rigid(h);
             sph_launch_boundary(h, SPH_MATERIAL_FLUID);
             if ((rc = sph_sort_particles(h))) return rc;
-            sph_launch_density(h);
-            sph_launch_dfsph_alpha(h);
+            sph_launch_density(h, true);   // + compute_alpha on the same staged windows
             if ((rc = dfsph_correct_divergence_error(h, &it, &e))) return rc;
             st->dfsph_iterations_v = it; st->dfsph_divergence_error = e; st->total_dfsph_iterations_v += it;
             break;
@@ -454,19 +457,22 @@ int sph_create(const SphParams* p, SphHandle** out) {
         const char* e = getenv("SPH_B200_NO_LISTS");
         h->lists_enabled = !(e && e[0] == '1');
         const char* k = getenv("SPH_B200_KMAX");
-        d.nbr_kmax = k ? atoi(k) : 96;
-        if (d.nbr_kmax < 1) d.nbr_kmax = 1;
-        d.nbr_stride = (int)((n + 31) / 32 * 32);
-        if (h->lists_enabled) { ALLOC(d.nbr, (size_t)d.nbr_kmax * (size_t)d.nbr_stride); }
-        ALLOC(d.nbr_count, n);
-        ALLOC(d.chunk_desc, (n / SPH_BLOCK + 2) * 40);
-        ALLOC(d.win_stats, 4);
-        ALLOC(d.recA, n);
-        ALLOC(d.recB, n);
-        const char* w = getenv("SPH_B200_WMAX");   // window slots per CTA (16 B x payload arrays each)
-        h->wmax = w ? atoi(w) : 1536;
+        d.nbr_kmax = k ? atoi(k) : 64;
+        d.nbr_kmax = (d.nbr_kmax + 15) / 16 * 16;     // rows are read 16 slots (one 256-bit load) at a time
+        if (d.nbr_kmax < 16) d.nbr_kmax = 16;
+        if (h->lists_enabled) { ALLOC(d.nbr16, (size_t)d.nbr_kmax * n + 64); }
+        ALLOC(d.aux, n);
+        c.nbx = (c.nx + BRK_X - 1) / BRK_X; c.nby = (c.ny + BRK_Y - 1) / BRK_Y; c.nbz = (c.nz + BRK_Z - 1) / BRK_Z;
+        h->nbricks = c.nbx * c.nby * c.nbz;
+        ALLOC(d.brick_flag, (size_t)h->nbricks);
+        ALLOC(d.brick_list, (size_t)h->nbricks);
+        ALLOC(d.brick_ctl, BCTL_COUNT);
+        const char* w = getenv("SPH_B200_WMAX");   // window slots per brick (16 B x staged arrays each)
+        h->wmax = w ? atoi(w) : 2304;
         if (h->wmax < 64) h->wmax = 64;
-        if (h->wmax > 4096) h->wmax = 4096;
+        if (h->wmax > 4608) h->wmax = 4608;           // 3 arrays x 4608 x 16 B = 216 KB
+        const char* bi = getenv("SPH_B200_BATCH_ITERS");
+        h->solve_batch = bi ? atoi(bi) : 0;
     }
     if (!rc) {
         h->staging_bytes = (n ? n : 1) * 36;
@@ -501,6 +507,7 @@ int sph_destroy(SphHandle* h) {
 
 int sph_synchronize(SphHandle* h) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return SPH_OK;
 }
@@ -508,6 +515,7 @@ int sph_synchronize(SphHandle* h) {
 int sph_add_particles(SphHandle* h, int32_t object_id, int32_t n, const float* x, const float* v, const float* density,
                       const float* pressure, const int32_t* material, const int32_t* is_dynamic, const int32_t* color) {
     if (!h || n < 0) return SPH_E_INVALID;
+    ON_DEVICE(h);
     if (n == 0) return SPH_OK;
     if (!x || !v || !density || !pressure || !material || !is_dynamic || !color) return fail(h, SPH_E_INVALID, "null array");
     Consts& c = h->c;
@@ -539,7 +547,6 @@ int sph_add_particles(SphHandle* h, int32_t object_id, int32_t n, const float* x
     c.N += n;
     h->sorted_valid = false;
     h->list_valid = false;
-    h->rec_pos_valid = h->rec_vel_valid = false;
     h->rigid_volume_clean = false;
     h->dyn_rigid_dirty = true;
     return SPH_OK;
@@ -547,6 +554,7 @@ int sph_add_particles(SphHandle* h, int32_t object_id, int32_t n, const float* x
 
 int sph_get_field(SphHandle* h, int32_t field, void* dst, size_t bytes) {
     if (!h || !dst) return SPH_E_INVALID;
+    ON_DEVICE(h);
     FieldInfo fi = field_info(field);
     if (!fi.ok) return fail(h, SPH_E_INVALID, "unknown field");
     const size_t item = (size_t)fi.comps * 4;
@@ -572,6 +580,7 @@ int sph_get_field(SphHandle* h, int32_t field, void* dst, size_t bytes) {
 
 int sph_set_field(SphHandle* h, int32_t field, const void* src, size_t bytes) {
     if (!h || !src) return SPH_E_INVALID;
+    ON_DEVICE(h);
     FieldInfo fi = field_info(field);
     if (!fi.ok || field == SPH_F_CELL || field == SPH_F_NEIGHBOR_COUNT) return fail(h, SPH_E_INVALID, "field not settable");
     const size_t item = (size_t)fi.comps * 4;
@@ -588,14 +597,14 @@ int sph_set_field(SphHandle* h, int32_t field, const void* src, size_t bytes) {
     if (field == SPH_F_POSITION) h->sorted_valid = false;
     if (field == SPH_F_POSITION || field == SPH_F_MATERIAL) h->list_valid = false;
     h->rigid_volume_clean = false;   // any host edit may touch what the boundary volumes depend on
-    if (field == SPH_F_POSITION || field == SPH_F_MATERIAL || field == SPH_F_REST_VOLUME) h->rec_pos_valid = false;
-    if (field == SPH_F_VELOCITY || field == SPH_F_MASS) h->rec_vel_valid = false;
     if (field == SPH_F_MATERIAL || field == SPH_F_IS_DYNAMIC) h->dyn_rigid_dirty = true;
+    if (field == SPH_F_MATERIAL || field == SPH_F_REST_VOLUME || field == SPH_F_OBJECT_ID) h->bricks_dirty = true;
     return SPH_OK;
 }
 
 int sph_fill_field(SphHandle* h, int32_t field, double value) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     FieldInfo fi = field_info(field);
     if (!fi.ok || field == SPH_F_CELL || field == SPH_F_NEIGHBOR_COUNT) return fail(h, SPH_E_INVALID, "field not settable");
     const size_t n = (size_t)h->c.cap;
@@ -607,10 +616,9 @@ int sph_fill_field(SphHandle* h, int32_t field, double value) {
     int comps = sph_staging_to_field(h, field, (int)n);
     if (comps < 0) return fail(h, comps, "field not available for this solver");
     if (field == SPH_F_MATERIAL || field == SPH_F_IS_DYNAMIC) h->dyn_rigid_dirty = true;
+    if (field == SPH_F_MATERIAL || field == SPH_F_REST_VOLUME || field == SPH_F_OBJECT_ID) h->bricks_dirty = true;
     if (field == SPH_F_POSITION || field == SPH_F_MATERIAL) h->list_valid = false;
     h->rigid_volume_clean = false;   // any host edit may touch what the boundary volumes depend on
-    if (field == SPH_F_POSITION || field == SPH_F_MATERIAL || field == SPH_F_REST_VOLUME) h->rec_pos_valid = false;
-    if (field == SPH_F_VELOCITY || field == SPH_F_MASS) h->rec_vel_valid = false;
     return last_launch(h);
 }
 
@@ -642,6 +650,7 @@ int sph_field_ptr(SphHandle* h, int32_t field, void** ptr, int32_t* stride, int3
 
 int sph_get_scalar(SphHandle* h, int32_t s, double* out) {
     if (!h || !out) return SPH_E_INVALID;
+    ON_DEVICE(h);
     int rc;
     switch (s) {
         case SPH_S_DT: *out = h->c.dt; break;
@@ -667,6 +676,13 @@ int sph_get_scalar(SphHandle* h, int32_t s, double* out) {
         case SPH_S_VISCOSITY_B: *out = h->P.viscosity_b; break;
         case SPH_S_NUM_CELLS: *out = h->c.ncell; break;
         case SPH_S_MAX_PARTICLES: *out = h->c.cap; break;
+        case SPH_S_ACTIVE_BRICKS: case SPH_S_MAX_WINDOW_SLOTS: case SPH_S_WINDOW_OVERFLOWS: {
+            int ctl[BCTL_COUNT];
+            CUDA_TRY(h, cudaMemcpyAsync(ctl, h->d.brick_ctl, sizeof ctl, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            *out = ctl[s == SPH_S_ACTIVE_BRICKS ? BCTL_ACTIVE : (s == SPH_S_MAX_WINDOW_SLOTS ? BCTL_WMAX_SEEN : BCTL_OVERFLOWS)];
+            break;
+        }
         default: return fail(h, SPH_E_INVALID, "unknown scalar");
     }
     return SPH_OK;
@@ -674,11 +690,12 @@ int sph_get_scalar(SphHandle* h, int32_t s, double* out) {
 
 int sph_set_scalar(SphHandle* h, int32_t s, double v) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     switch (s) {
         case SPH_S_DT: h->P.dt = v; refresh_consts(h); break;
         case SPH_S_PARTICLE_NUM:
             if (v < 0 || v > h->c.cap) return fail(h, SPH_E_CAPACITY, "particle_num out of range");
-            h->c.N = (int)v; h->rigid_volume_clean = false; h->sorted_valid = false; h->list_valid = false; h->rec_pos_valid = h->rec_vel_valid = false; break;
+            h->c.N = (int)v; h->rigid_volume_clean = false; h->sorted_valid = false; h->list_valid = false; break;
         case SPH_S_FLUID_PARTICLE_NUM: h->Nfluid = (int)v; break;
         case SPH_S_PCISPH_K: h->c.pcisph_k = (float)v; break;
         case SPH_S_DENSITY_ERROR: h->density_error = (float)v; break;
@@ -693,8 +710,10 @@ int sph_set_scalar(SphHandle* h, int32_t s, double v) {
 
 int sph_set_object(SphHandle* h, int32_t obj, int32_t material, int32_t is_dynamic) {
     if (!h || obj < 0 || obj >= SPH_MAX_OBJECTS) return SPH_E_INVALID;
+    ON_DEVICE(h);
     h->object_material[obj] = material;
     h->rigid_is_dynamic_h[obj] = is_dynamic;
+    h->bricks_dirty = true;   // emitter objects (fluid objects parked as rigid) count as working rows
     CUDA_TRY(h, cudaMemcpyAsync(h->d.object_material, h->object_material, sizeof h->object_material, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->d.rigid_is_dynamic, h->rigid_is_dynamic_h, sizeof h->rigid_is_dynamic_h, cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -704,6 +723,7 @@ int sph_set_object(SphHandle* h, int32_t obj, int32_t material, int32_t is_dynam
 int sph_set_rigid_state(SphHandle* h, int32_t obj, const float com0[3], const float com[3], const float rot[9],
                         const float vel[3], const float omega[3]) {
     if (!h || obj < 0 || obj >= SPH_MAX_OBJECTS) return SPH_E_INVALID;
+    ON_DEVICE(h);
     float* s = h->rigid_state_h[obj];
     if (com0) memcpy(s + 0, com0, 12);
     if (com) memcpy(s + 3, com, 12);
@@ -717,6 +737,7 @@ int sph_set_rigid_state(SphHandle* h, int32_t obj, const float com0[3], const fl
 
 int sph_get_rigid_wrench(SphHandle* h, float* force, float* torque) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     float w[SPH_MAX_OBJECTS * 6];
     CUDA_TRY(h, cudaMemcpyAsync(w, h->d.rigid_wrench, sizeof w, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -730,12 +751,14 @@ int sph_get_rigid_wrench(SphHandle* h, float* force, float* torque) {
 
 int sph_zero_rigid_wrench(SphHandle* h) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     CUDA_TRY(h, cudaMemsetAsync(h->d.rigid_wrench, 0, sizeof(float) * SPH_MAX_OBJECTS * 6, h->stream));
     return SPH_OK;
 }
 
 int sph_compute_rigid_body_mass(SphHandle* h, int32_t object_id, float* out) {
     if (!h || !out) return SPH_E_INVALID;
+    ON_DEVICE(h);
     int rc;
     if ((rc = zero_red(h, RED_MASS))) return rc;
     sph_launch_rigid_body_mass(h, object_id);
@@ -746,6 +769,7 @@ int sph_compute_rigid_body_mass(SphHandle* h, int32_t object_id, float* out) {
 
 int sph_prepare_neighborhood_search(SphHandle* h) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     rows_all(h);
     int rc = update_dynamic_rigid_flag(h);
     if (rc) return rc;
@@ -756,6 +780,7 @@ int sph_prepare_neighborhood_search(SphHandle* h) {
 
 int sph_get_neighbors(SphHandle* h, int32_t* offsets, int32_t* indices, size_t capacity) {
     if (!h || !offsets) return SPH_E_INVALID;
+    ON_DEVICE(h);
     const int N = h->c.N;
     int *counts = nullptr, *offs = nullptr, *idx = nullptr;
     CUDA_TRY(h, cudaMalloc((void**)&counts, sizeof(int) * (size_t)(N + 1)));
@@ -763,10 +788,10 @@ int sph_get_neighbors(SphHandle* h, int32_t* offsets, int32_t* indices, size_t c
     if (e != cudaSuccess) { cudaFree(counts); return check_cuda(h, e, "cudaMalloc"); }
     sph_launch_neighbor_count(h, counts);
     sph_exclusive_scan(h, counts, N, offs);
-    cudaMemcpyAsync(offsets, offs, sizeof(int) * (size_t)(N + 1), cudaMemcpyDeviceToHost, h->stream);
-    cudaStreamSynchronize(h->stream);
+    int rc = check_cuda(h, cudaMemcpyAsync(offsets, offs, sizeof(int) * (size_t)(N + 1), cudaMemcpyDeviceToHost, h->stream), "copy of the neighbour offsets");
+    if (!rc) rc = check_cuda(h, cudaStreamSynchronize(h->stream), "neighbour count");
     if (N == 0) offsets[0] = 0;
-    int rc = last_launch(h);
+    if (!rc) rc = last_launch(h);
     if (!rc && indices) {
         const size_t total = (size_t)offsets[N];
         if (total > capacity) rc = fail(h, SPH_E_CAPACITY, "indices capacity too small");
@@ -775,9 +800,9 @@ int sph_get_neighbors(SphHandle* h, int32_t* offsets, int32_t* indices, size_t c
             if (e != cudaSuccess) rc = check_cuda(h, e, "cudaMalloc");
             else {
                 sph_launch_neighbor_fill(h, offs, idx);
-                cudaMemcpyAsync(indices, idx, sizeof(int) * total, cudaMemcpyDeviceToHost, h->stream);
-                cudaStreamSynchronize(h->stream);
-                rc = last_launch(h);
+                rc = check_cuda(h, cudaMemcpyAsync(indices, idx, sizeof(int) * total, cudaMemcpyDeviceToHost, h->stream), "copy of the neighbour indices");
+                if (!rc) rc = check_cuda(h, cudaStreamSynchronize(h->stream), "neighbour fill");
+                if (!rc) rc = last_launch(h);
             }
         }
     }
@@ -788,6 +813,7 @@ int sph_get_neighbors(SphHandle* h, int32_t* offsets, int32_t* indices, size_t c
 
 int sph_get_grid_num_particles(SphHandle* h, int32_t* dst, size_t count) {
     if (!h || !dst || count > (size_t)h->c.ncell) return SPH_E_INVALID;
+    ON_DEVICE(h);
     // per-cell histogram in the reference's z-fastest flatten, inclusive-scanned (base_container.py:546)
     int *hist = nullptr, *scan = nullptr;
     const size_t nc = (size_t)h->c.ncell;
@@ -797,15 +823,16 @@ int sph_get_grid_num_particles(SphHandle* h, int32_t* dst, size_t count) {
     cudaMemsetAsync(hist, 0, sizeof(int) * (nc + 8), h->stream);
     sph_launch_ref_cell_hist(h, hist);
     sph_exclusive_scan(h, hist, (int)nc, scan);
-    cudaMemcpyAsync(dst, scan + 1, sizeof(int) * count, cudaMemcpyDeviceToHost, h->stream);   // inclusive = exclusive shifted by one
-    cudaStreamSynchronize(h->stream);
-    int rc = last_launch(h);
+    int rc = check_cuda(h, cudaMemcpyAsync(dst, scan + 1, sizeof(int) * count, cudaMemcpyDeviceToHost, h->stream), "copy of the cell counts");   // inclusive = exclusive shifted by one
+    if (!rc) rc = check_cuda(h, cudaStreamSynchronize(h->stream), "cell histogram");
+    if (!rc) rc = last_launch(h);
     cudaFree(hist); cudaFree(scan);
     return rc;
 }
 
 int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     rows_all(h);
     if (h->slab && ((task >= SPH_T_CG_PREPARE1 && task <= SPH_T_COPY_BACK_ORIGINAL_VELOCITY) || task >= SPH_T_PCISPH_COMPUTE_PREDICTED_VELOCITY))
         return fail(h, SPH_E_UNSUPPORTED, "Z-slab handles support WCSPH and DFSPH with standard viscosity");
@@ -831,7 +858,7 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
         case SPH_T_COMPUTE_PRESSURE_ACCELERATION: sph_launch_pressure_accel(h); break;
         case SPH_T_COMPUTE_GRAVITY_ACCELERATION: sph_launch_gravity(h); break;
         case SPH_T_COMPUTE_SURFACE_TENSION_ACCELERATION: sph_launch_surface_tension(h); break;
-        case SPH_T_COMPUTE_VISCOSITY_ACCELERATION_STANDARD: sph_launch_viscosity(h, false); break;
+        case SPH_T_COMPUTE_VISCOSITY_ACCELERATION_STANDARD: sph_launch_viscosity(h); break;
         case SPH_T_COMPUTE_DENSITY: sph_launch_density(h); break;
         case SPH_T_ENFORCE_DOMAIN_BOUNDARY_3D: sph_launch_boundary(h, iarg); break;
         case SPH_T_RENEW_RIGID_PARTICLE_STATE: sph_launch_renew_rigid(h); break;
@@ -886,9 +913,13 @@ int sph_run_task(SphHandle* h, int32_t task, int32_t iarg, float* out) {
 
 int sph_step(SphHandle* h, int32_t n_steps, SphStepStats* stats) {
     if (!h || n_steps < 0) return SPH_E_INVALID;
+    ON_DEVICE(h);
     rows_all(h);
     if (h->slab && (h->P.method == SPH_METHOD_PCISPH || h->P.visc_method == SPH_VISC_IMPLICIT))
         return fail(h, SPH_E_UNSUPPORTED, "Z-slab handles support WCSPH and DFSPH with standard viscosity");
+    // a DFSPH step begins with sweeps on the grid of the previous step's sort (DFSPH.py:298-319)
+    if (h->P.method == SPH_METHOD_DFSPH && !h->sorted_valid && n_steps > 0)
+        return fail(h, SPH_E_STATE, "particles were added or moved by the host since the last sort: call prepare_neighborhood_search() first");
     int rc = update_dynamic_rigid_flag(h);
     if (rc) return rc;
     SphStepStats st;
@@ -906,6 +937,7 @@ int sph_step(SphHandle* h, int32_t n_steps, SphStepStats* stats) {
 
 int sph_dfsph_correct_density_error(SphHandle* h, int32_t* it, float* e) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     rows_all(h);
     int i; float err;
     int rc = dfsph_correct_density_error(h, &i, &err);
@@ -915,6 +947,7 @@ int sph_dfsph_correct_density_error(SphHandle* h, int32_t* it, float* e) {
 }
 int sph_dfsph_correct_divergence_error(SphHandle* h, int32_t* it, float* e) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     rows_all(h);
     int i; float err;
     int rc = dfsph_correct_divergence_error(h, &i, &err);
@@ -924,6 +957,7 @@ int sph_dfsph_correct_divergence_error(SphHandle* h, int32_t* it, float* e) {
 }
 int sph_pcisph_refine(SphHandle* h, int32_t* it, float* e) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     rows_all(h);
     int i; float err;
     int rc = pcisph_refine(h, &i, &err);
@@ -933,6 +967,7 @@ int sph_pcisph_refine(SphHandle* h, int32_t* it, float* e) {
 }
 int sph_implicit_viscosity_solve(SphHandle* h, int32_t* it, float* e) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     rows_all(h);
     if (h->P.visc_method != SPH_VISC_IMPLICIT) return fail(h, SPH_E_STATE, "viscosityMethod is not implicit");
     int i; float err;
@@ -944,6 +979,7 @@ int sph_implicit_viscosity_solve(SphHandle* h, int32_t* it, float* e) {
 
 int sph_set_stream(SphHandle* h, void* cuda_stream) {
     if (!h) return SPH_E_INVALID;
+    ON_DEVICE(h);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
     return SPH_OK;
@@ -957,21 +993,22 @@ int sph_profile_enable(SphHandle* h, int32_t enable) {
 
 int sph_profile_read(SphHandle* h, SphKernelStat* out, int32_t capacity, int32_t* count) {
     if (!h || !count) return SPH_E_INVALID;
+    ON_DEVICE(h);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     int n = 0;
     for (auto& r : h->prof) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.begin, r.end) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
-        const char* name = r.name;
-        if (!strncmp(name, "(", 1)) name++;   // macro arguments may arrive parenthesised
+        char name[sizeof out[0].name];   // macro arguments may arrive parenthesised: "(kb_build<true, true, false>)"
+        memset(name, 0, sizeof name);
+        strncpy(name, r.name + (r.name[0] == '(' ? 1 : 0), sizeof name - 1);
+        if (char* paren = strchr(name, ')')) *paren = 0;
         int k = 0;
-        for (; k < n; k++) if (!strncmp(out[k].name, name, sizeof out[k].name - 1)) break;
+        for (; k < n; k++) if (!strncmp(out[k].name, name, sizeof name - 1)) break;
         if (k == n) {
             if (n >= capacity || !out) { h->event_pool.push_back(r.begin); h->event_pool.push_back(r.end); continue; }
             memset(&out[n], 0, sizeof out[n]);
-            strncpy(out[n].name, name, sizeof out[n].name - 1);
-            char* paren = strchr(out[n].name, ')');
-            if (paren) *paren = 0;
+            memcpy(out[n].name, name, sizeof name);
             n++;
         }
         out[k].launches++;

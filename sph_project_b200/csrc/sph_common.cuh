@@ -40,19 +40,15 @@ struct Consts {
     float diameter, diameter2, w_diameter;  // 2 dx, its square, W(2 dx)  (base_solver.py:222-229)
     float dom_x, dom_y, dom_z, padding;
     float pcisph_k;
+    float corr_thresh;   // m_eps * dt of the DFSPH correction steps (DFSPH.py:175,258)
     int z_lo, z_hi;   // owned cell layers (whole grid unless the handle is a slab)
     int row_begin, row_end;   // rows the kernels update: [0, N) or, for a Z-slab, the owned index range
+    int nbx, nby, nbz;        // brick grid: ceil(grid_num / SPH_BRICK_{X,Y,Z})  (sph_brick.cuh)
 };
 
 // per-particle work happens for owned rows only; ghost rows (Z-slabs) are read-only neighbours
 #define SPH_ROW_OR_RETURN(c, i) if ((i) < (c).row_begin || (i) >= (c).row_end) return
 #define SPH_IS_ROW(c, i) ((i) >= (c).row_begin && (i) < (c).row_end)
-
-// 32-byte neighbour record: one 256-bit load (LDG.E.256, sm_100+) fetches everything a sweep needs
-// about neighbour j.  lo = pv (x, y, z, +-V); hi = the per-sweep payload.
-struct __align__(32) Rec {
-    float4 lo, hi;
-};
 
 // device pointers; `cur` selects the live half of the ping-pong buffers
 struct Dev {
@@ -87,50 +83,21 @@ struct Dev {
     float* rigid_wrench;      // [20][6] force, torque
     // reductions
     double* red;              // small scratch for block reductions [64]
-    // per-particle neighbour lists, valid while positions are frozen (sort .. next position update):
-    // nbr[k * nbr_stride + i] = sorted index of the k-th neighbour of fluid particle i (coalesced along
-    // i), nbr_count[i] entries (rows with more than nbr_kmax re-derive their neighbours), walk order
-    int* nbr;
-    int* nbr_count;
-    int nbr_stride;
-    int nbr_kmax;
-    int* chunk_desc;          // SPH_DESC_INTS per chunk of SPH_BLOCK sorted particles (list build)
-    int* win_stats;           // [0] max window entries over chunks, [1] chunks above the smem budget
-    // neighbour records gathered by the list-based sweeps (copies of the canonical arrays):
-    //   recA[j] = {pv_j, vm_j}                    velocity sweeps (density change, viscosity, CG setup)
-    //   recB[j] = {pv_j, (s0, s1, rho_j, m_j)}    scalar sweeps; (s0, s1) = (kappa, kappa/rho) for the
-    //                                              DFSPH correction, (p/rho^2, p) for the pressure force
-    Rec* recA;
-    Rec* recB;
+    // per-particle neighbour lists, valid while positions are frozen (sort .. next position update), row-major:
+    // row i = nbr16[i * nbr_kmax ..]: word 0 = number of neighbours n of fluid particle i, words 1 .. n = the WINDOW
+    // SLOTS (16 bit) of its neighbours inside the shared-memory window of the brick that owns i (sph_brick.cuh), in walk
+    // order.  n = 0xffff marks a row without a list (more than nbr_kmax - 1 neighbours, a window beyond 16 bits, a
+    // particle that left its sorted cell): such rows re-derive their neighbours by walking the 27 cells in global memory.
+    unsigned short* nbr16;
+    int nbr_kmax;             // multiple of 16 (one 256-bit load = 16 slots)
+    // bricks (compact tiles of SPH_BRICK_X x Y x Z cells, one CTA each): flags set by the sort's gather, compacted list
+    int* brick_flag;          // [nbricks] brick owns at least one fluid(-to-be) row
+    int* brick_list;          // [nbricks] active brick ids, ascending
+    int* brick_ctl;           // [0] active count  [1] ticket  [2] CTAs finished  [3] max window slots seen  [4] windows above the smem budget
+    // per-sweep scalar payload of neighbour j, staged next to pv_j: (s0, s1, rho_j, m_j) with (s0, s1) =
+    // (kappa, kappa / rho) for the DFSPH correction steps, (p / rho^2, p) for the pressure force
+    float4* aux;
 };
-
-// one 256-bit read-only gather of a neighbour record
-__device__ __forceinline__ void ldg_rec(const Rec* p, float4& lo, float4& hi) {
-#if defined(SPH_REC_L2_EVICT_LAST) && defined(SPH_REC_EVICT_LAST)   // variant builds: cache-residency hints for the records,
-    asm("ld.global.nc.L1::evict_last.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"   // which neighbouring lanes / warps re-read
-#elif defined(SPH_REC_L2_EVICT_LAST)   // (the L2 hint exists for 256-bit loads only; the 4-byte list stream cannot carry one)
-    asm("ld.global.nc.L2::evict_last.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#elif defined(SPH_REC_EVICT_LAST)
-    asm("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#else
-    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-#endif
-        : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w), "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w)
-        : "l"(p));
-}
-
-// neighbour-list index load (streamed once per sweep).  Variant build SPH_IDX_NO_ALLOCATE keeps it out of the L1 so
-// that the lines stay available to the record gathers.
-#ifdef SPH_IDX_NO_ALLOCATE
-__device__ __forceinline__ int ldg_idx_no_allocate(const int* p) {
-    int v;
-    asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-}
-#define SPH_LDG_IDX(ptr) ldg_idx_no_allocate(ptr)
-#else
-#define SPH_LDG_IDX(ptr) __ldg(ptr)
-#endif
 
 // ---- small vector helpers -------------------------------------------------------------------
 __device__ __forceinline__ float3 f3(float4 a) { return make_float3(a.x, a.y, a.z); }
@@ -157,7 +124,8 @@ __device__ __forceinline__ float kernel_W_q(const Consts& c, float q) {
 }
 // gradient = R * kernel_gradient_scale(r2): zero for r <= 1e-5 (and beyond the support)
 __device__ __forceinline__ float kernel_gradient_scale(const Consts& c, float r2) {
-    float rinv = rsqrtf(r2);
+    float rinv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(r2));   // r2 is far above the denormals wherever the result is used
     float r = r2 * rinv;
     float q = r * c.inv_h;
     float t = 1.0f - q;
@@ -234,16 +202,18 @@ struct SphHandle {
     bool dyn_rigid_dirty = true;
     bool lists_enabled = true;   // SPH_B200_NO_LISTS=1 forces window walks (A/B testing)
     bool list_valid = false;     // nbr lists match the current positions and order
+    bool bricks_dirty = false;   // materials were edited by the host since the sort flagged the working bricks
     bool rigid_volume_clean = false;   // static boundary volumes are current (nothing added / edited since)
-    bool rec_pos_valid = false;  // recA.lo / recB.lo mirror pv
-    bool rec_vel_valid = false;  // recA.hi mirrors vm
     // Z-slab state (sph_slab.cu); ghost_stale = fields whose ghost copies lag their owners
     struct SlabState* slab = nullptr;
     long long n_global = 0;
     int ghost_stale = 0;
     bool rows_from_sort = false; // owned range was set by a slab sort (host edits must not widen it to the ghosts)
     int sticky_rc = 0;           // first error raised inside a void launcher (NCCL), reported by the caller
-    int wmax = 1536;             // shared-memory window budget (slots) of the sweep kernels
+    int wmax = 2304;             // shared-memory window budget (slots per brick) of the sweep kernels
+    int nbricks = 0;
+    int solve_hint[2] = {2, 2};  // iterations the last DFSPH density / divergence solve took: size of the next first batch
+    int solve_batch = 0;         // > 0: fixed number of solver iterations per host read (SPH_B200_BATCH_ITERS)
     // per-kernel event timing (sph_profile_enable / sph_profile_read)
     cudaStream_t own_stream = nullptr;
     bool profiling = false;

@@ -8,8 +8,11 @@
 //     the oracle's order) by a tiny per-cell sort of the scattered permutation, so runs are
 //     bit-reproducible although the histogram ranks come from atomics;
 //   * fields are gathered once into the other half of a ping-pong pair (156 B/particle of traffic
-//     instead of the reference's scatter + copy-back, 304 B/particle).
+//     instead of the reference's scatter + copy-back, 304 B/particle);
+//   * the gather also flags the bricks (compact tiles of cells, sph_brick.cuh) that own fluid rows; a one-block scan
+//     compacts them into the work list of the persistent sweep kernels.
 #include "sph_kernels.h"
+#include "sph_brick.cuh"
 
 namespace {
 
@@ -131,82 +134,70 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_sort_cells(Consts c, Dev d) {
     }
 }
 
-// One block = one chunk of the sweep kernels: also counts the chunk's fluid rows (descriptor [2]).
+// Gather of every persistent field into the other half of its ping-pong pair.  Also flags the bricks (sph_brick.cuh)
+// that own at least one row a sweep will work on: fluid particles, and emitter particles that are parked as rigid until
+// they cross gravitationUpper (base_solver.py:651-677) and may turn fluid before the next sort.
 __global__ void __launch_bounds__(SPH_BLOCK) k_gather(Consts c, Dev d, int with_ghost_slot) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = k < c.N ? d.perm[k] : 0;
-    float4 pv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k < c.N) pv = d.pv[i];
-    const int nfluid = __syncthreads_count(pv.w > 0.0f);
-    if (threadIdx.x == 0) d.chunk_desc[(size_t)blockIdx.x * 40 + 2] = nfluid;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= c.N) return;
-    const float4 vm = d.vm[i];
+    const int i = d.perm[k];
+    const float4 pv = d.pv[i];
+    const int obj = d.object_id[i];
+    const int flat = d.grid_id[i];
     d.pv_alt[k] = pv;
-    d.vm_alt[k] = vm;
-    Rec ra; ra.lo = pv; ra.hi = vm;
-    d.recA[k] = ra;          // neighbour records of the list-based sweeps (sph_sweeps.cu)
-    d.recB[k].lo = pv;
+    d.vm_alt[k] = d.vm[i];
     d.x0_alt[3 * k + 0] = d.x0[3 * i + 0];
     d.x0_alt[3 * k + 1] = d.x0[3 * i + 1];
     d.x0_alt[3 * k + 2] = d.x0[3 * i + 2];
     d.rho_alt[k] = d.rho[i];
-    d.object_id_alt[k] = d.object_id[i];
+    d.object_id_alt[k] = obj;
     d.material_alt[k] = d.material[i];
     d.color_alt[3 * k + 0] = d.color[3 * i + 0];
     d.color_alt[3 * k + 1] = d.color[3 * i + 1];
     d.color_alt[3 * k + 2] = d.color[3 * i + 2];
     d.is_dynamic_alt[k] = d.is_dynamic[i];
-    d.grid_id_alt[k] = d.grid_id[i];
+    d.grid_id_alt[k] = flat;
     d.uid_alt[k] = d.uid[i];
     if (with_ghost_slot) d.ghost_slot_alt[k] = d.ghost_slot[i];
+    bool works = pv.w > 0.0f;
+    if (!works && obj >= 0 && obj < SPH_MAX_OBJECTS) works = d.object_material[obj] == SPH_MATERIAL_FLUID;
+    if (works && SPH_IS_ROW(c, k) && flat < c.ncell) {
+        const int cx = flat % c.nx, cy = (flat / c.nx) % c.ny, cz = flat / (c.nx * c.ny);
+        d.brick_flag[((cz / BRK_Z) * c.nby + cy / BRK_Y) * c.nbx + cx / BRK_X] = 1;   // same value from every writer
+    }
 }
 
-// Window descriptor of every chunk (layout in sph_window.cuh): the <= 9 index ranges of the sorted
-// arrays that cover the 27-cell neighbourhoods of the chunk's particles, overlapping ranges merged.
-// Runs after the gather (reads the new grid ids); one thread per chunk.
-__global__ void __launch_bounds__(SPH_BLOCK) k_chunk_windows(Consts c, Dev d, int nchunks, int wmax) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= nchunks) return;
-    const int first = ch * SPH_BLOCK, last = min(first + SPH_BLOCK, c.N) - 1;
-    const int c0 = d.grid_id[first], c1 = d.grid_id[last];
-    int* desc = d.chunk_desc + (size_t)ch * 40;
-    int ncp = 0, total = 0;
-    int cur_g = 0, cur_e = 0, cur_s = 0;
-    for (int r = 0; r < 9; r++) {
-        const int off = ((r / 3 - 1) * c.ny + (r % 3 - 1)) * c.nx;   // (dz, dy) row offset
-        const int lo = max(c0 + off - 1, 0), hi = min(c1 + off + 1, c.ncell - 1);
-        int g = 0, e = 0;
-        if (lo <= hi) {
-            g = d.cell_start[lo];
-            e = d.cell_start[hi + 1];
-        }
-        if (e <= g) {   // empty range: never indexed
-            desc[4 + r] = 0;
-            desc[13 + r] = 0;
-            continue;
-        }
-        if (ncp > 0 && g <= cur_e) {   // overlaps / touches the current copy: extend it
-            desc[4 + r] = g;
-            desc[13 + r] = cur_s + (g - cur_g);
-            if (e > cur_e) {
-                total += e - cur_e;
-                cur_e = e;
-                desc[31 + ncp - 1] = cur_e - cur_g;
-            }
-        } else {
-            cur_g = g; cur_e = e; cur_s = total;
-            desc[22 + ncp] = g;
-            desc[31 + ncp] = e - g;
-            ncp++;
-            total += e - g;
-            desc[4 + r] = g;
-            desc[13 + r] = cur_s;
-        }
+// Same flags from the sorted arrays (host edits of materials after the sort)
+__global__ void __launch_bounds__(SPH_BLOCK) k_flag_bricks(Consts c, Dev d) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= c.N || !SPH_IS_ROW(c, k)) return;
+    const int obj = d.object_id[k], flat = d.grid_id[k];
+    bool works = d.pv[k].w > 0.0f;
+    if (!works && obj >= 0 && obj < SPH_MAX_OBJECTS) works = d.object_material[obj] == SPH_MATERIAL_FLUID;
+    if (works && flat < c.ncell) {
+        const int cx = flat % c.nx, cy = (flat / c.nx) % c.ny, cz = flat / (c.nx * c.ny);
+        d.brick_flag[((cz / BRK_Z) * c.nby + cy / BRK_Y) * c.nbx + cx / BRK_X] = 1;
     }
-    desc[0] = total;
-    desc[1] = ncp;
-    atomicMax(d.win_stats + 0, total);
-    if (total > wmax) atomicAdd(d.win_stats + 1, 1);
+}
+
+// Ascending list of the flagged bricks + the control words of the persistent brick kernels (one block).
+__global__ void __launch_bounds__(1024) k_brick_compact(Dev d, int nbricks) {
+    int carry = 0;
+    for (int base = 0; base < nbricks; base += 1024) {
+        const int b = base + threadIdx.x;
+        const int f = b < nbricks ? (d.brick_flag[b] != 0) : 0;
+        int total;
+        const int ex = block_exclusive_scan(f, &total);
+        if (f) d.brick_list[carry + ex] = b;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        d.brick_ctl[BCTL_ACTIVE] = carry;
+        d.brick_ctl[BCTL_TICKET] = 0;
+        d.brick_ctl[BCTL_FINISHED] = 0;
+        d.brick_ctl[BCTL_WMAX_SEEN] = 0;
+        d.brick_ctl[BCTL_OVERFLOWS] = 0;
+    }
 }
 
 }  // namespace
@@ -222,6 +213,17 @@ void sph_exclusive_scan(SphHandle* h, const int* in, int n, int* out) {
     { SphProf p(h, "k_scan_sums"); k_scan_sums<<<1, 1024, 0, h->stream>>>(h->d.scan_tmp, tiles); }
     { SphProf p(h, "k_scan_final"); k_scan_final<<<tiles, SCAN_THREADS, 0, h->stream>>>(in, n, h->d.scan_tmp, out); }
     h->launches += 3;
+}
+
+// re-derive the brick work list when materials were edited since the sort
+void sph_bricks_refresh(SphHandle* h) {
+    if (!h->bricks_dirty) return;
+    h->bricks_dirty = false;
+    if (!h->sorted_valid) return;   // the next sort rebuilds it
+    cudaMemsetAsync(h->d.brick_flag, 0, sizeof(int) * (size_t)h->nbricks, h->stream);
+    if (h->c.N > 0) k_flag_bricks<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d);
+    k_brick_compact<<<1, 1024, 0, h->stream>>>(h->d, h->nbricks);
+    h->launches += 2;
 }
 
 template <class T>
@@ -255,6 +257,7 @@ int sph_sort_particles(SphHandle* h) {
     }
     if (c.N > 0) {
         { SphProf p(h, "k_sort_cells"); k_sort_cells<<<(c.ncell + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, st>>>(c, d); }
+        cudaMemsetAsync(d.brick_flag, 0, sizeof(int) * (size_t)h->nbricks, st);
         { SphProf p(h, "k_gather"); k_gather<<<nb, SPH_BLOCK, 0, st>>>(c, d, slab ? 1 : 0); }
         h->launches += 2;
         swap_ptr(d.pv, d.pv_alt);
@@ -268,17 +271,17 @@ int sph_sort_particles(SphHandle* h) {
         swap_ptr(d.grid_id, d.grid_id_alt);
         swap_ptr(d.uid, d.uid_alt);
         swap_ptr(d.ghost_slot, d.ghost_slot_alt);
-        cudaMemsetAsync(d.win_stats, 0, 2 * sizeof(int), st);
-        {
-            SphProf p(h, "k_chunk_windows");
-            k_chunk_windows<<<(nb + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, st>>>(c, d, nb, h->wmax);
-            h->launches++;
-        }
+    } else {
+        cudaMemsetAsync(d.brick_flag, 0, sizeof(int) * (size_t)h->nbricks, st);
+    }
+    {
+        SphProf p(h, "k_brick_compact");
+        k_brick_compact<<<1, 1024, 0, st>>>(d, h->nbricks);
+        h->launches++;
     }
     h->sorted_valid = true;
+    h->bricks_dirty = false;
     h->list_valid = false;
-    h->rec_pos_valid = c.N > 0;
-    h->rec_vel_valid = c.N > 0;
     h->ghost_stale = 0;   // the ghosts were just re-imported with their owners' current state
     return cudaGetLastError() == cudaSuccess ? SPH_OK : SPH_E_CUDA;
 }

@@ -11,15 +11,14 @@ enum RedSlot {
     RED_CG_PAP = 3,     // sum p . Ap
     RED_CG_RR_NEW = 4,  // sum |r_new|^2 (numerator of beta, cg_error^2)
     RED_CG_RR_OLD = 5,  // sum |r_old|^2 (denominator of beta)
-    RED_COUNT = 16
+    // loop control of the DFSPH solves when the exit test runs on the device (sph_sweeps.cu, SolveMode)
+    CTRL_DONE = 32,     // != 0: the solve has converged; speculative launches return at once
+    CTRL_ITERS = 33,    // iterations tested so far
+    CTRL_ERR = 34,      // average error of the last tested iteration
+    CTRL_COUNT = 3,
+    RED_COUNT = 48
 };
 
-#ifdef SPH_DEVICE_CONVERGENCE
-// Variant build: the DFSPH density solve tests convergence on the device, so the host reads the result
-// once per batch of iterations instead of once per iteration.  Control words live in spare slots of Dev::red.
-enum SolveCtrlSlot { CTRL_DONE = 32, CTRL_ITERS = 33, CTRL_ERR = 34, CTRL_COUNT = 3 };
-void sph_launch_dfsph_solve_check(SphHandle* h, float n_global, float eta);
-#endif
 
 #ifdef __CUDACC__
 // sum `v` over the block, one atomicAdd(double) per block
@@ -55,20 +54,23 @@ void sph_ghost_sync(SphHandle* h, int what);
 // sph_grid.cu
 void sph_exclusive_scan(SphHandle* h, const int* in, int n, int* out);
 int sph_sort_particles(SphHandle* h);
+void sph_bricks_refresh(SphHandle* h);   // brick work list after host edits of materials
 
 // sph_sweeps.cu
 void sph_launch_rigid_volume(SphHandle* h);
-void sph_launch_density(SphHandle* h);
+void sph_launch_density(SphHandle* h, bool with_alpha = false);   // with_alpha: DFSPH compute_alpha on the same staged window
 void sph_launch_pressure_accel(SphHandle* h);
 void sph_launch_temp_pressure_accel(SphHandle* h);
 void sph_launch_surface_tension(SphHandle* h);
-void sph_launch_viscosity(SphHandle* h, bool aux_ready);   // aux_ready: aux already holds (., ., rho, m)
+void sph_launch_viscosity(SphHandle* h);
 void sph_launch_dfsph_alpha(SphHandle* h);
-void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused);   // fused: + kappa_v + error sum
-void sph_launch_dfsph_density_star(SphHandle* h, bool fused);         // fused: + kappa + error sum
+// fused: + kappa(_v) + aux payload; mode (SolveMode: 0 plain, 1 error sum, 2 error sum + exit test on the device),
+// speculative: return at once when an earlier launch of the batch has converged
+void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused, int mode = 0, bool speculative = false, float eta = 0.0f);
+void sph_launch_dfsph_density_star(SphHandle* h, bool fused, int mode = 0, bool speculative = false, float eta = 0.0f);
 bool sph_lists_ready(SphHandle* h);
-void sph_launch_dfsph_correct_divergence(SphHandle* h, bool aux_ready);   // aux_ready: fused kernel wrote kappa into aux
-void sph_launch_dfsph_correct_density(SphHandle* h, bool aux_ready);
+void sph_launch_dfsph_correct_divergence(SphHandle* h, bool aux_ready, bool speculative = false);   // aux_ready: fused kernel wrote kappa into aux
+void sph_launch_dfsph_correct_density(SphHandle* h, bool aux_ready, bool speculative = false);
 void sph_launch_pcisph_density_star(SphHandle* h);
 void sph_launch_cg_prepare1(SphHandle* h);
 void sph_launch_cg_Ap(SphHandle* h, bool aux_ready);

@@ -12,8 +12,12 @@
 //
 // Once per step, before the sort, particles that left the slab migrate to the neighbour and the
 // ghost layers are re-imported (full particle records); inside the solver loops only the fields a
-// sweep's inputs changed are refreshed: recA (velocities) and recB (kappa) twice per DFSPH iteration,
-// plus one ncclAllReduce of the error sum.  All NCCL calls are enqueued on the handle's stream.
+// sweep's inputs changed are refreshed: vm (velocities) and aux (kappa), 16 bytes per ghost each, once per DFSPH
+// iteration, plus one ncclAllReduce of the error sum.  All NCCL calls are enqueued on the handle's stream.
+//
+// Every decision that leads to a collective or point-to-point call is the same on all ranks: the kernels a step
+// launches depend on the solver, on iteration counts (all-reduced), and on two flags — "some rank holds dynamic rigid
+// particles" and "some rank's boundary volumes are out of date" — that are summed over the ranks at every sort.
 //
 // NCCL is resolved at run time from the process (torch has already loaded libnccl.so.2); the
 // communicator is created from a unique id that the Python host broadcasts with torch.distributed.
@@ -204,7 +208,7 @@ int exchange_phase(SphHandle* h, int mode, int slot) {
         NCCL_TRY(h, g_nccl.Recv(s->d_counts + 2 + side, 1, ncclInt32, nbr, s->comm, st));
     }
     NCCL_TRY(h, g_nccl.GroupEnd());
-    CU_TRY(h, cudaMemcpyAsync(s->h_ints, s->d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(s->h_ints, s->d_counts, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));   // counts + the uniform flags
     CU_TRY(h, cudaStreamSynchronize(st));
     const int send_n[2] = {s->h_ints[0], s->h_ints[1]}, recv_n[2] = {s->h_ints[2], s->h_ints[3]};
     for (int side = 0; side < 2; side++)
@@ -230,7 +234,8 @@ int exchange_phase(SphHandle* h, int mode, int slot) {
         h->launches++;
     }
     s->halo_bytes += (int64_t)(send_n[0] + send_n[1]) * REC_WORDS * 4;
-    return cudaGetLastError() == cudaSuccess ? SPH_OK : fail(h, SPH_E_CUDA, cudaGetErrorString(cudaGetLastError()));
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPH_OK : fail(h, SPH_E_CUDA, cudaGetErrorString(e));
 }
 
 }  // namespace
@@ -239,8 +244,19 @@ bool sph_is_slab(const SphHandle* h) { return h->slab != nullptr && h->slab->com
 
 // Migration + ghost re-import, run by the sort path right before the cell histogram.
 int sph_slab_pre_sort(SphHandle* h) {
+    SlabState* s = h->slab;
+    // rank-uniform flags (read back with the first count exchange): [4] dynamic rigid particles anywhere,
+    // [5] boundary volumes stale anywhere
+    s->h_ints[16] = 0;
+    s->h_ints[17] = h->rigid_volume_clean ? 0 : 1;
+    CU_TRY(h, cudaMemcpyAsync(s->d_counts + 4, s->h_ints + 16, 2 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    sph_launch_count_dynamic_rigid(h, s->d_counts + 4);
+    NCCL_TRY(h, g_nccl.AllReduce(s->d_counts + 4, s->d_counts + 4, 2, ncclInt32, ncclSum, s->comm, h->stream));
     int rc = exchange_phase(h, 0, SLOT_OWNED);
     if (rc) return rc;
+    h->c.has_dynamic_rigid = s->h_ints[4] > 0 ? 1 : 0;
+    h->dyn_rigid_dirty = false;
+    if (s->h_ints[5] > 0) h->rigid_volume_clean = false;
     return exchange_phase(h, 1, SLOT_GHOST);
 }
 

@@ -27,7 +27,6 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_update_velocity(Consts c, Dev d) 
     const float4 a = d.acc[i];
     v.x += c.dt * a.x; v.y += c.dt * a.y; v.z += c.dt * a.z;
     d.vm[i] = v;
-    d.recA[i].hi = v;   // keep the neighbour record current (read by the next velocity sweep)
 }
 
 // update_fluid_position (base_solver.py:651-666) incl. the emitter branch
@@ -351,10 +350,10 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_ref_cell_hist(Consts c, Dev d, in
 
 void sph_launch_gravity(SphHandle* h) { LAUNCH_N(k_gravity, h->c.N, h->c, h->d); }
 void sph_launch_update_velocity(SphHandle* h) { LAUNCH_N(k_update_velocity, h->c.N, h->c, h->d); sph_ghost_dirty(h, GHOST_VEL); }
-void sph_launch_update_position(SphHandle* h) { LAUNCH_N(k_update_position, h->c.N, h->c, h->d); h->list_valid = false; h->rec_pos_valid = false; sph_ghost_dirty(h, GHOST_PV); }
-void sph_launch_boundary(SphHandle* h, int t) { LAUNCH_N(k_boundary, h->c.N, h->c, h->d, t); h->list_valid = false; h->rec_pos_valid = false; h->rec_vel_valid = false; sph_ghost_dirty(h, GHOST_PV | GHOST_VEL); }
-void sph_launch_renew_rigid(SphHandle* h) { LAUNCH_N(k_renew_rigid, h->c.N, h->c, h->d); h->list_valid = false; h->rec_pos_valid = false; h->rec_vel_valid = false; }
-void sph_launch_prepare_emitter(SphHandle* h) { LAUNCH_N(k_prepare_emitter, h->c.N, h->c, h->d); h->list_valid = false; h->rec_pos_valid = false; }
+void sph_launch_update_position(SphHandle* h) { LAUNCH_N(k_update_position, h->c.N, h->c, h->d); h->list_valid = false; sph_ghost_dirty(h, GHOST_PV); }
+void sph_launch_boundary(SphHandle* h, int t) { LAUNCH_N(k_boundary, h->c.N, h->c, h->d, t); h->list_valid = false; sph_ghost_dirty(h, GHOST_PV | GHOST_VEL); }
+void sph_launch_renew_rigid(SphHandle* h) { LAUNCH_N(k_renew_rigid, h->c.N, h->c, h->d); h->list_valid = false; sph_ghost_dirty(h, GHOST_PV | GHOST_VEL); }
+void sph_launch_prepare_emitter(SphHandle* h) { LAUNCH_N(k_prepare_emitter, h->c.N, h->c, h->d); h->list_valid = false; sph_ghost_dirty(h, GHOST_PV); }
 void sph_launch_wcsph_pressure(SphHandle* h) { LAUNCH_N(k_wcsph_pressure, h->c.N, h->c, h->d); sph_ghost_dirty(h, GHOST_RHO); }
 void sph_launch_dfsph_kappa_v(SphHandle* h) { LAUNCH_N(k_dfsph_kappa_v, h->c.N, h->c, h->d); }
 void sph_launch_dfsph_kappa(SphHandle* h) { LAUNCH_N(k_dfsph_kappa, h->c.N, h->c, h->d); }
@@ -371,8 +370,8 @@ void sph_launch_cg_update_x(SphHandle* h) { LAUNCH_N(k_cg_update_x, h->c.N, h->c
 void sph_launch_cg_update_r(SphHandle* h) { LAUNCH_N(k_cg_update_r, h->c.N, h->c, h->d); }
 void sph_launch_cg_update_p(SphHandle* h) { LAUNCH_N(k_cg_update_p, h->c.N, h->c, h->d); }
 void sph_launch_cg_prepare_guess(SphHandle* h) { LAUNCH_N(k_cg_prepare_guess, h->c.N, h->c, h->d); }
-void sph_launch_cg_velocity_from_x(SphHandle* h) { LAUNCH_N(k_cg_velocity<false>, h->c.N, h->c, h->d); h->rec_vel_valid = false; }
-void sph_launch_cg_velocity_restore(SphHandle* h) { LAUNCH_N(k_cg_velocity<true>, h->c.N, h->c, h->d); h->rec_vel_valid = false; }
+void sph_launch_cg_velocity_from_x(SphHandle* h) { LAUNCH_N(k_cg_velocity<false>, h->c.N, h->c, h->d); sph_ghost_dirty(h, GHOST_VEL); }
+void sph_launch_cg_velocity_restore(SphHandle* h) { LAUNCH_N(k_cg_velocity<true>, h->c.N, h->c, h->d); sph_ghost_dirty(h, GHOST_VEL); }
 void sph_launch_rigid_body_mass(SphHandle* h, int obj) { LAUNCH_N(k_rigid_body_mass, h->c.N, h->c, h->d, obj); }
 void sph_launch_count_dynamic_rigid(SphHandle* h, int* out) { LAUNCH_N(k_count_dynamic_rigid, h->c.N, h->c, h->d, out); }
 void sph_fill_i32(SphHandle* h, int* p, size_t n, int v) { LAUNCH_N(k_fill_i32, n, p, n, v); }

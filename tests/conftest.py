@@ -11,17 +11,6 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "slow: takes more than a few seconds on CPU")
-    config.addinivalue_line("markers", "gpu_next: GPU tests written after the round's GPU budget was spent; not yet run on hardware")
-
-
-def pytest_collection_modifyitems(config, items):
-    """`gpu_next` tests run only on request (SPH_RUN_GPU_NEXT=1)."""
-    if os.environ.get("SPH_RUN_GPU_NEXT") == "1":
-        return
-    skip = pytest.mark.skip(reason="gpu_next: not yet validated on hardware (set SPH_RUN_GPU_NEXT=1)")
-    for item in items:
-        if "gpu_next" in item.keywords:
-            item.add_marker(skip)
 
 
 def pytest_sessionstart(session):

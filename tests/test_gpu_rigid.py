@@ -1,18 +1,12 @@
-"""Dynamic rigid bodies on the CUDA path against the oracle (wrench atomics, renew_rigid_particle_state).
-
-Written after round 1's GPU budget was spent, so it has not run on hardware yet: it is skipped unless
-SPH_RUN_GPU_NEXT=1 (run `SPH_RUN_GPU_NEXT=1 pytest -m gpu tests/test_gpu_next_rigid.py` on a B200 box,
-then drop the guard)."""
-import os
-
+"""Dynamic rigid bodies on the CUDA path against the oracle (wrench atomics, renew_rigid_particle_state);
+reference: base_solver.py:174-187, 272-278, 615-629, DFSPH.py:190-202, 270-283."""
 import numpy as np
 import pytest
 
 from helpers import by_uid, make_sim, oracle_library
 from test_rigid_stepper import cube_scene
 
-pytestmark = [pytest.mark.gpu, pytest.mark.gpu_next,
-              pytest.mark.skipif(os.environ.get("SPH_RUN_GPU_NEXT") != "1", reason="not yet validated on hardware")]
+pytestmark = pytest.mark.gpu
 
 
 def test_dynamic_cube_matches_oracle(tmp_path):

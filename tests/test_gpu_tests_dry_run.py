@@ -8,11 +8,11 @@ import sys
 
 from helpers import ROOT
 
-FILES = ["test_ref_golden.py", "test_golden.py", "test_run_simulation.py", "test_gpu_next_rigid.py", "test_gpu_parity.py"]
+FILES = ["test_ref_golden.py", "test_golden.py", "test_run_simulation.py", "test_gpu_rigid.py", "test_gpu_parity.py"]
 
 
 def run(extra):
-    env = dict(os.environ, SPH_GPU_TESTS_DRY_RUN="1", SPH_RUN_GPU_NEXT="1")
+    env = dict(os.environ, SPH_GPU_TESTS_DRY_RUN="1")
     return subprocess.run([sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + extra,
                           cwd=os.path.join(ROOT, "tests"), env=env, capture_output=True, text=True, timeout=900)
 

@@ -223,8 +223,7 @@ def test_cuda_matches_reference_sources(name, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.gpu_next          # mesh bodies / dynamic rigid bodies are SURVEY 8(f2, f3) "next" rows, not yet run on
-@pytest.mark.parametrize("name", NEXT_ROWS)   # hardware: opt in with SPH_RUN_GPU_NEXT=1
+@pytest.mark.parametrize("name", NEXT_ROWS)   # mesh bodies / dynamic rigid bodies: SURVEY 8(f2, f3), a17
 def test_cuda_rigid_coupling_matches_reference_sources(name, tmp_path):
     g, sc = load(name, tmp_path)
     c, s = build(sc, None, g)
