@@ -467,8 +467,10 @@ int sph_create(const SphParams* p, SphHandle** out) {
         ALLOC(d.brick_flag, (size_t)h->nbricks);
         ALLOC(d.brick_list, (size_t)h->nbricks);
         ALLOC(d.brick_ctl, BCTL_COUNT);
+        ALLOC(d.brick_nf, (size_t)h->nbricks);
+        if (h->lists_enabled) { ALLOC(d.row_order, n + 64); }
         const char* w = getenv("SPH_B200_WMAX");   // window slots per brick (16 B x staged arrays each)
-        h->wmax = w ? atoi(w) : 2304;
+        h->wmax = w ? atoi(w) : 2112;                 // 4 x 4 x 3 cells + halo = 180 cells x 10 particles at rest density + 17 %
         if (h->wmax < 64) h->wmax = 64;
         if (h->wmax > 4608) h->wmax = 4608;           // 3 arrays x 4608 x 16 B = 216 KB
         const char* bi = getenv("SPH_B200_BATCH_ITERS");

@@ -1,7 +1,8 @@
 // sph_brick.cuh — compact CTA tiles ("bricks") with TMA-staged shared-memory windows for every neighbour sweep.
 //
-// A brick is SPH_BRICK_X x SPH_BRICK_Y x SPH_BRICK_Z cells of the uniform grid (default 4 x 4 x 4: ~512 fluid
-// particles at rest density).  Its particles and the particles of the one-cell halo around it — the 27-cell
+// A brick is SPH_BRICK_X x SPH_BRICK_Y x SPH_BRICK_Z cells of the uniform grid (default 4 x 4 x 3: 48 cells, ~480
+// fluid particles at rest density — a cell of edge h = 4 r holds 10 particles of volume 0.8 (2 r)^3 — i.e. one row
+// per thread of a 512-thread CTA with a little head-room).  Its particles and the particles of the one-cell halo around it — the 27-cell
 // neighbourhoods of everything the brick owns — are (BY + 2)(BZ + 2) contiguous runs of the cell-sorted arrays,
 // because the flatten is x-fastest: run (y, z) covers cells x0-1 .. x0+BX of that grid row.  One CTA works on one
 // brick at a time:
@@ -11,10 +12,15 @@
 //      copies (cp.async.bulk + mbarrier; SASS UBLKCP), one copy per run and array, issued by the first 36 threads;
 //   3. every owned fluid particle streams its neighbour list — 16-bit WINDOW SLOTS, 16 per 256-bit load — and reads
 //      neighbour j's position and payload from shared memory (LDS.128) instead of gathering it through the L1.
-// The halo makes the window (BX+2)(BY+2)(BZ+2) / (BX BY BZ) = 3.4x the owned data (the round-1 chunks of 128
+// The halo makes the window (BX+2)(BY+2)(BZ+2) / (BX BY BZ) = 3.75x the owned data (the round-1 chunks of 128
 // consecutive particles were 1 x 1 x 13-cell sticks: ~10x).  CTAs are persistent: they draw bricks from a ticket
 // counter over the compacted list of bricks that own fluid rows (built by the sort), so boundary-only and empty
 // bricks cost nothing and the tail is balanced dynamically.
+//
+// Load balance inside a CTA (measured on 4 x 4 x 4 bricks = 640 rows per 512 threads: the four warps with a second
+// pass kept the other twelve at the end-of-brick barrier, 28 % of all warp time): bricks are sized to at most one row
+// per thread, the list build leaves a stably compacted list of the brick's working rows (no lanes parked on boundary
+// particles), and warps draw groups of 32 consecutive rows of it from a shared counter.
 //
 // Rows without a usable list (more than nbr_kmax neighbours, a window beyond 16 bits, a particle that left its sorted
 // cell since the sort) and windows that exceed the shared-memory budget fall back to global memory with the same
@@ -31,10 +37,16 @@
 #define SPH_BRICK_Y 4
 #endif
 #ifndef SPH_BRICK_Z
-#define SPH_BRICK_Z 4
+#define SPH_BRICK_Z 3
 #endif
 #ifndef SPH_BRICK_THREADS
 #define SPH_BRICK_THREADS 512
+#endif
+// Neighbours whose shared-memory loads are issued together.  Measured on B200 (profiles/r02_brick_experiments.md):
+// batches of 4 need 64 registers, i.e. two instead of three resident CTAs per SM, and lose more to the missing warps
+// (186 / 202 us per correction / density-change sweep) than they gain from the overlap (168 / 181 us unbatched).
+#ifndef SPH_BRICK_ILP
+#define SPH_BRICK_ILP 1
 #endif
 
 constexpr int BRK_X = SPH_BRICK_X, BRK_Y = SPH_BRICK_Y, BRK_Z = SPH_BRICK_Z;
@@ -44,6 +56,8 @@ constexpr int BRK_OWN_RUNS = BRK_Y * BRK_Z;      // runs that hold owned particl
 constexpr int BRK_TW = BRK_X + 3;                // cell_start entries per run: cells x0-1 .. x0+BX and the end
 constexpr int BRK_CELLS = BRK_X * BRK_Y * BRK_Z;
 constexpr int BRK_WARPS = SPH_BRICK_THREADS / 32;
+constexpr int BRK_SORT_PASSES = 4;                                   // rows per thread the build can compact
+constexpr int BRK_ROWS_MAX = BRK_SORT_PASSES * SPH_BRICK_THREADS;   // owned particles per brick beyond which the row list is not built
 static_assert(BRK_RUNS <= SPH_BRICK_THREADS, "one thread per run issues the TMA copies");
 
 enum BrickCtl { BCTL_ACTIVE = 0, BCTL_TICKET = 1, BCTL_FINISHED = 2, BCTL_WMAX_SEEN = 3, BCTL_OVERFLOWS = 4, BCTL_COUNT = 8 };
@@ -105,24 +119,36 @@ __device__ __forceinline__ float4 lds64(unsigned addr) {   // first two componen
 }
 
 // ---- per-CTA brick state in shared memory -----------------------------------------------------------
+// Tables of one brick.  Two sets per CTA: while the CTA works on one brick, warp 0 prepares the tables of the next,
+// so a single barrier and the TMA round trip are all that separates two bricks.
 struct BrickShared {
-    unsigned long long mbar;
     int T[BRK_RUNS][BRK_TW];     // T[r][k] = cell_start of cell x0-1+k in run r (sorted indices); all 0 for rows outside the grid
     int S[BRK_RUNS + 1];         // window slot of the first particle of run r (prefix of the run lengths)
     int OP[BRK_OWN_RUNS + 1];    // prefix of the owned-run lengths: flat owned index -> run
-    int brick;                   // current brick id, -1 when the ticket counter ran out
+    int brick;                   // brick id, -1 when the ticket counter ran out
+    int ordinal;                 // its position in the active list (index of brick_nf)
+    int nf;                      // working rows in the compacted row list (row_order), -1: none, walk the owned rows as they come
+    int group;                   // next group of 32 listed rows to hand out
     int staged;                  // window is in shared memory (else: same slots, fetched from global memory)
     int x0, y0, z0;              // first owned cell
 };
+struct BrickSmem {
+    unsigned long long mbar;
+    BrickShared tab[2];
+};
 
 struct Brick {
-    BrickShared* sh;
+    BrickSmem* smem;
+    BrickShared* sh;             // tables of the brick in hand
     unsigned a0, a1, a2;         // shared addresses of the staged arrays (a0 = pv window), 16 B per slot
     const float4* g0;            // their global sources
     const float4* g1;
     const float4* g2;
     unsigned phase;              // mbarrier parity of the next wait
-    int b_pre, t_pre;            // thread 0: prefetched brick id (next brick) and ticket (the one after)
+    int parity;                  // which table set is in hand
+    int wmax;
+    bool stage, sorted;
+    int b_pre, o_pre, nf_pre, t_pre;   // thread 0: prefetched brick id, ordinal, listed-row count (brick after next) and ticket (the one after)
 };
 
 // one owned particle: sorted index and window slot
@@ -156,43 +182,136 @@ __device__ __forceinline__ int brick_slot_to_index(const BrickShared& sh, int sl
 }
 __device__ __forceinline__ int brick_nbr_index(const Brick& bk, NbrRef ref) { return ref.is_slot ? brick_slot_to_index(*bk.sh, ref.v) : ref.v; }
 
-__device__ __forceinline__ int brick_list_entry(const Dev& d, int ticket) {
-    return ticket < d.brick_ctl[BCTL_ACTIVE] ? __ldg(d.brick_list + ticket) : -1;
+// thread 0: brick id / ordinal / listed rows of ticket `ticket` (loads issued now, consumed one brick later)
+__device__ __forceinline__ void brick_prefetch(const Dev& d, Brick& bk, int ticket) {
+    const bool live = ticket < d.brick_ctl[BCTL_ACTIVE];
+    bk.o_pre = ticket;
+    bk.b_pre = live ? __ldg(d.brick_list + ticket) : -1;
+    bk.nf_pre = (live && bk.sorted) ? d.brick_nf[ticket] : -1;
 }
 
-// CTA-wide: set up the barrier once per kernel; thread 0 draws its first tickets
-__device__ __forceinline__ void brick_init(Brick& bk, BrickShared* sh, float4* smem, int wmax, const float4* g0, const float4* g1,
-                                           const float4* g2) {
-    bk.sh = sh;
-    bk.a0 = smem_u32(smem); bk.a1 = bk.a0 + 16u * (unsigned)wmax; bk.a2 = bk.a1 + 16u * (unsigned)wmax;
-    bk.g0 = g0; bk.g1 = g1; bk.g2 = g2;
-    bk.phase = 0;
-    bk.b_pre = -1; bk.t_pre = 0;
-    if (threadIdx.x == 0) {
-        mbar_init(&sh->mbar, 1);
-        fence_mbar_init();
-    }
-}
-__device__ __forceinline__ void brick_first_tickets(const Dev& d, Brick& bk) {
-    if (threadIdx.x == 0) {
-        bk.b_pre = brick_list_entry(d, atomicAdd(d.brick_ctl + BCTL_TICKET, 1));
-        bk.t_pre = atomicAdd(d.brick_ctl + BCTL_TICKET, 1);
-    }
-}
-
-// CTA-wide: draw the next active brick; false when there is none left.  The ticket counter and the brick list are read
-// one and two bricks ahead (thread 0 keeps them in registers), so no global-memory latency sits between two bricks.
-__device__ __forceinline__ bool brick_next(const Dev& d, Brick& bk) {
-    __syncthreads();   // everyone is done with the previous window and its tables
-    if (threadIdx.x == 0) {
-        bk.sh->brick = bk.b_pre;
-        if (bk.b_pre >= 0) {
-            bk.b_pre = brick_list_entry(d, bk.t_pre);
+// warp 0: tables of the brick thread 0 has prefetched, into `tab`; thread 0 then prefetches the one after
+__device__ __forceinline__ void brick_prepare(const Consts& c, const Dev& d, Brick& bk, BrickShared& tab) {
+    const int lane = threadIdx.x;   // warp 0
+    const int b = __shfl_sync(0xffffffffu, bk.b_pre, 0);
+    const int ordinal = __shfl_sync(0xffffffffu, bk.o_pre, 0);
+    const int nf = __shfl_sync(0xffffffffu, bk.nf_pre, 0);
+    if (lane == 0) {
+        tab.brick = b;
+        tab.ordinal = ordinal;
+        tab.nf = nf;
+        tab.group = 0;
+        if (b >= 0) {
+            brick_prefetch(d, bk, bk.t_pre);
             bk.t_pre = atomicAdd(d.brick_ctl + BCTL_TICKET, 1);
         }
     }
+    if (b >= 0) {
+        const int bx = b % c.nbx, by = (b / c.nbx) % c.nby, bz = b / (c.nbx * c.nby);
+        const int x0 = bx * BRK_X, y0 = by * BRK_Y, z0 = bz * BRK_Z;
+#pragma unroll 1
+        for (int e = lane; e < BRK_RUNS * BRK_TW; e += 32) {
+            const int r = e / BRK_TW, k = e - r * BRK_TW;
+            const int y = y0 - 1 + r % BRK_RY, z = z0 - 1 + r / BRK_RY;
+            int v = 0;
+            if (y >= 0 && y < c.ny && z >= 0 && z < c.nz) {
+                const int x = min(max(x0 - 1 + k, 0), c.nx);   // x == nx: end of the grid row
+                v = __ldg(d.cell_start + ((z * c.ny + y) * c.nx + x));
+            }
+            tab.T[r][k] = v;
+        }
+        __syncwarp();
+        int carry = 0;   // prefix sums of the run lengths (window slots) and of the owned-run lengths
+#pragma unroll
+        for (int r0 = 0; r0 < BRK_RUNS; r0 += 32) {
+            const int r = r0 + lane;
+            const int len = r < BRK_RUNS ? tab.T[r][BRK_TW - 1] - tab.T[r][0] : 0;
+            const int inc = brk_warp_inclusive_scan(len);
+            if (r < BRK_RUNS) tab.S[r] = carry + inc - len;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        int ocarry = 0;
+#pragma unroll
+        for (int q0 = 0; q0 < BRK_OWN_RUNS; q0 += 32) {
+            const int q = q0 + lane;
+            int len = 0;
+            if (q < BRK_OWN_RUNS) {
+                const int r = (q / BRK_Y + 1) * BRK_RY + (q % BRK_Y + 1);
+                len = tab.T[r][BRK_X + 1] - tab.T[r][1];
+            }
+            const int inc = brk_warp_inclusive_scan(len);
+            if (q < BRK_OWN_RUNS) tab.OP[q] = ocarry + inc - len;
+            ocarry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            tab.S[BRK_RUNS] = carry;
+            tab.OP[BRK_OWN_RUNS] = ocarry;
+            tab.staged = bk.stage && carry <= bk.wmax;
+            tab.x0 = x0; tab.y0 = y0; tab.z0 = z0;
+            if (carry > d.brick_ctl[BCTL_WMAX_SEEN]) atomicMax(d.brick_ctl + BCTL_WMAX_SEEN, carry);
+            if (bk.stage && carry > bk.wmax) atomicAdd(d.brick_ctl + BCTL_OVERFLOWS, 1);
+        }
+    }
+    __syncwarp();
+}
+
+// CTA-wide, once per kernel: barrier, first tickets, tables of the first brick.
+// stage: copy windows into shared memory; sorted: walk the rows through the list build's row lists.
+__device__ __forceinline__ void brick_begin(const Consts& c, const Dev& d, Brick& bk, BrickSmem* smem, float4* window, int wmax,
+                                            const float4* g0, const float4* g1, const float4* g2, bool stage, bool sorted) {
+    bk.smem = smem;
+    bk.a0 = smem_u32(window); bk.a1 = bk.a0 + 16u * (unsigned)wmax; bk.a2 = bk.a1 + 16u * (unsigned)wmax;
+    bk.g0 = g0; bk.g1 = g1; bk.g2 = g2;
+    bk.phase = 0;
+    bk.parity = 0;
+    bk.wmax = wmax;
+    bk.stage = stage; bk.sorted = sorted;
+    bk.b_pre = -1; bk.o_pre = 0; bk.nf_pre = -1; bk.t_pre = 0;
+    bk.sh = &smem->tab[0];
+    if (threadIdx.x == 0) {
+        mbar_init(&smem->mbar, 1);
+        fence_mbar_init();
+        brick_prefetch(d, bk, atomicAdd(d.brick_ctl + BCTL_TICKET, 1));
+        bk.t_pre = atomicAdd(d.brick_ctl + BCTL_TICKET, 1);
+    }
+    if (threadIdx.x < 32) brick_prepare(c, d, bk, smem->tab[0]);
     __syncthreads();
-    return bk.sh->brick >= 0;
+}
+
+// CTA-wide: false when the bricks have run out; else the window of the brick in hand is staged (NARR arrays by TMA
+// bulk copies, budget permitting) and warp 0 has prepared the tables of the next brick.
+template <int NARR>
+__device__ __forceinline__ bool brick_stage(const Consts& c, const Dev& d, Brick& bk) {
+    BrickShared& sh = *bk.sh;
+    if (sh.brick < 0) return false;
+    const int tid = threadIdx.x;
+    if (sh.staged) {
+        // lane 0 of every warp issues the copies of runs warp, warp + BRK_WARPS, ...: the issue is spread over the four
+        // schedulers instead of being serialised inside one warp (UBLKCP takes its operands from uniform registers)
+        for (int r = (tid & 31) ? BRK_RUNS : (tid >> 5); r < BRK_RUNS; r += BRK_WARPS) {
+            const int g = sh.T[r][0], n = sh.T[r][BRK_TW - 1] - g, s = sh.S[r];
+            if (n > 0) {
+                tma_bulk_load(bk.a0 + 16u * s, bk.g0 + g, (unsigned)n * 16u, &bk.smem->mbar);
+                if (NARR > 1) tma_bulk_load(bk.a1 + 16u * s, bk.g1 + g, (unsigned)n * 16u, &bk.smem->mbar);
+                if (NARR > 2) tma_bulk_load(bk.a2 + 16u * s, bk.g2 + g, (unsigned)n * 16u, &bk.smem->mbar);
+            }
+        }
+        // the phase cannot complete before this arrival, whatever the copies have already delivered
+        if (tid == 0) mbar_arrive_expect_tx(&bk.smem->mbar, (unsigned)sh.S[BRK_RUNS] * 16u * NARR);
+    }
+    if (tid < 32) brick_prepare(c, d, bk, bk.smem->tab[bk.parity ^ 1]);   // overlaps the copies
+    if (sh.staged) {
+        mbar_wait(&bk.smem->mbar, bk.phase);
+        bk.phase ^= 1u;
+    }
+    return true;
+}
+
+// CTA-wide: done with the brick in hand (its window and tables may be overwritten); the next one is in the other set
+__device__ __forceinline__ void brick_advance(Brick& bk) {
+    __syncthreads();
+    bk.parity ^= 1;
+    bk.sh = &bk.smem->tab[bk.parity];
 }
 
 // CTA-wide, once at the end of the kernel: the last CTA to finish re-arms the ticket counter for the next launch.
@@ -214,76 +333,6 @@ __device__ __forceinline__ bool brick_finish(const Dev& d) {
     return last;
 }
 
-// CTA-wide: tables of the current brick and, budget permitting, its window of NARR arrays staged by TMA
-template <int NARR>
-__device__ __forceinline__ void brick_open(const Consts& c, const Dev& d, Brick& bk, int wmax, bool stage) {
-    BrickShared& sh = *bk.sh;
-    const int tid = threadIdx.x;
-    const int b = sh.brick;
-    const int bx = b % c.nbx, by = (b / c.nbx) % c.nby, bz = b / (c.nbx * c.nby);
-    const int x0 = bx * BRK_X, y0 = by * BRK_Y, z0 = bz * BRK_Z;
-    for (int e = tid; e < BRK_RUNS * BRK_TW; e += SPH_BRICK_THREADS) {
-        const int r = e / BRK_TW, k = e - r * BRK_TW;
-        const int y = y0 - 1 + r % BRK_RY, z = z0 - 1 + r / BRK_RY;
-        int v = 0;
-        if (y >= 0 && y < c.ny && z >= 0 && z < c.nz) {
-            const int x = min(max(x0 - 1 + k, 0), c.nx);   // x == nx: end of the grid row
-            v = __ldg(d.cell_start + (size_t)(z * c.ny + y) * c.nx + x);
-        }
-        sh.T[r][k] = v;
-    }
-    __syncthreads();
-    if (tid < 32) {   // warp 0: prefix sums of the run lengths (window slots) and of the owned-run lengths
-        int carry = 0;
-#pragma unroll
-        for (int r0 = 0; r0 < BRK_RUNS; r0 += 32) {
-            const int r = r0 + tid;
-            const int len = r < BRK_RUNS ? sh.T[r][BRK_TW - 1] - sh.T[r][0] : 0;
-            const int inc = brk_warp_inclusive_scan(len);
-            if (r < BRK_RUNS) sh.S[r] = carry + inc - len;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        int ocarry = 0;
-#pragma unroll
-        for (int q0 = 0; q0 < BRK_OWN_RUNS; q0 += 32) {
-            const int q = q0 + tid;
-            int len = 0;
-            if (q < BRK_OWN_RUNS) {
-                const int r = (q / BRK_Y + 1) * BRK_RY + (q % BRK_Y + 1);
-                len = sh.T[r][BRK_X + 1] - sh.T[r][1];
-            }
-            const int inc = brk_warp_inclusive_scan(len);
-            if (q < BRK_OWN_RUNS) sh.OP[q] = ocarry + inc - len;
-            ocarry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (tid == 0) {
-            sh.S[BRK_RUNS] = carry;
-            sh.OP[BRK_OWN_RUNS] = ocarry;
-            sh.staged = stage && carry <= wmax;
-            sh.x0 = x0; sh.y0 = y0; sh.z0 = z0;
-            if (carry > d.brick_ctl[BCTL_WMAX_SEEN]) atomicMax(d.brick_ctl + BCTL_WMAX_SEEN, carry);
-            if (stage && carry > wmax) atomicAdd(d.brick_ctl + BCTL_OVERFLOWS, 1);
-        }
-    }
-    __syncthreads();
-    if (sh.staged) {
-        // lane 0 of every warp issues the copies of runs warp, warp + BRK_WARPS, ...: the issue is spread over the four
-        // schedulers instead of being serialised inside one warp (UBLKCP takes its operands from uniform registers)
-        for (int r = (tid & 31) ? BRK_RUNS : (tid >> 5); r < BRK_RUNS; r += BRK_WARPS) {
-            const int g = sh.T[r][0], n = sh.T[r][BRK_TW - 1] - g, s = sh.S[r];
-            if (n > 0) {
-                tma_bulk_load(bk.a0 + 16u * s, bk.g0 + g, (unsigned)n * 16u, &sh.mbar);
-                if (NARR > 1) tma_bulk_load(bk.a1 + 16u * s, bk.g1 + g, (unsigned)n * 16u, &sh.mbar);
-                if (NARR > 2) tma_bulk_load(bk.a2 + 16u * s, bk.g2 + g, (unsigned)n * 16u, &sh.mbar);
-            }
-        }
-        // the phase cannot complete before this arrival, whatever the copies have already delivered
-        if (tid == 0) mbar_arrive_expect_tx(&sh.mbar, (unsigned)sh.S[BRK_RUNS] * 16u * NARR);
-        mbar_wait(&sh.mbar, bk.phase);
-        bk.phase ^= 1u;
-    }
-}
-
 __device__ __forceinline__ int brick_own_count(const Brick& bk) { return bk.sh->OP[BRK_OWN_RUNS]; }
 
 // flat owned index t -> sorted particle index + window slot (branch-free: broadcast reads of the 16-entry prefix)
@@ -291,7 +340,7 @@ __device__ __forceinline__ BrickRow brick_own_row(const Brick& bk, int t) {
     const BrickShared& sh = *bk.sh;
     int q = 0;
 #pragma unroll
-    for (int k = 1; k < BRK_OWN_RUNS; k++) q += (t >= sh.OP[k]) ? 1 : 0;
+    for (int k = 1; k < BRK_OWN_RUNS; k++) q += (t >= sh.OP[k]) ? 1 : 0;   // t < OP[BRK_OWN_RUNS] is the caller's business
     const int r = (q / BRK_Y + 1) * BRK_RY + (q % BRK_Y + 1);
     const int off = t - sh.OP[q];
     BrickRow row;
@@ -314,7 +363,8 @@ __device__ __forceinline__ float4 brick_own_load(const Brick& bk, BrickRow row, 
 // All neighbours j of owned particle i in walk order: visit(ref, pj, aj, bj, R, r2), aj / bj = entry j of the second /
 // third staged array (pv_j itself when the sweep stages fewer).  Returns the number of neighbours.
 // A_HALF: the visitor reads only the first two components of aj (64-bit shared loads).
-template <bool LIST, bool NC, int NARR, bool A_HALF = false, class Visit>
+// ILP: neighbours whose shared-memory loads are issued together (registers permitting).
+template <bool LIST, bool NC, int NARR, bool A_HALF = false, int ILP = SPH_BRICK_ILP, class Visit>
 __device__ __forceinline__ int brick_neighbors(const Consts& c, const Dev& d, const Brick& bk, int i, float4 pi, Visit&& visit) {
     if (LIST) {
         const unsigned short* row = d.nbr16 + (size_t)i * d.nbr_kmax;
@@ -330,20 +380,38 @@ __device__ __forceinline__ int brick_neighbors(const Consts& c, const Dev& d, co
                 asm volatile("mov.u32 %0, %0;" : "+r"(a0));
                 if (NARR > 1) asm volatile("mov.u32 %0, %0;" : "+r"(a1));
                 if (NARR > 2) asm volatile("mov.u32 %0, %0;" : "+r"(a2));
-                // one 256-bit load per 16 words; its latency is covered by the other resident warps (no register
-                // double-buffering: the kernels are held to 40 registers for three 512-thread CTAs per SM)
+                // One 256-bit load per 16 words, then batches of ILP neighbours: all shared-memory loads of a
+                // batch are issued before the first neighbour is evaluated (the per-neighbour branches would otherwise
+                // keep the compiler from overlapping them; measured: short-scoreboard stalls on one LDS at a time).
+                // Words past the end of the list load slot 0 (always inside the window) and are skipped.
                 int base = 0;
 #pragma unroll 1
                 for (;;) {
 #pragma unroll
-                    for (int u = 0; u < 16; u++) {
-                        if ((u > 0 || base > 0) && base + u <= n) {
-                            const unsigned off = (u & 1) ? ((w[u >> 1] >> 12) & 0xffff0u) : ((w[u >> 1] << 4) & 0xffff0u);   // 16 x slot
-                            const float4 pj = lds128(a0 + off);
-                            const float4 aj = NARR > 1 ? (A_HALF ? lds64(a1 + off) : lds128(a1 + off)) : pj;
-                            const float4 bj = NARR > 2 ? lds128(a2 + off) : pj;
-                            const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-                            visit(NbrRef{(int)(off >> 4), true}, pj, aj, bj, R, dist2(R));
+                    for (int u0 = 0; u0 < 16; u0 += ILP) {
+                        if (base + u0 > n) break;
+                        unsigned off[ILP];
+                        bool ok[ILP];
+                        float4 pj[ILP], aj[ILP], bj[ILP];
+#pragma unroll
+                        for (int k = 0; k < ILP; k++) {
+                            const int u = u0 + k;
+                            ok[k] = (u > 0 || base > 0) && base + u <= n;
+                            const unsigned o16 = (u & 1) ? ((w[u >> 1] >> 12) & 0xffff0u) : ((w[u >> 1] << 4) & 0xffff0u);   // 16 x slot
+                            off[k] = ok[k] ? o16 : 0u;
+                        }
+#pragma unroll
+                        for (int k = 0; k < ILP; k++) {
+                            pj[k] = lds128(a0 + off[k]);
+                            aj[k] = NARR > 1 ? (A_HALF ? lds64(a1 + off[k]) : lds128(a1 + off[k])) : pj[k];
+                            bj[k] = NARR > 2 ? lds128(a2 + off[k]) : pj[k];
+                        }
+#pragma unroll
+                        for (int k = 0; k < ILP; k++) {
+                            if (ok[k]) {
+                                const float3 R = make_float3(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z);
+                                visit(NbrRef{(int)(off[k] >> 4), true}, pj[k], aj[k], bj[k], R, dist2(R));
+                            }
                         }
                     }
                     base += 16;

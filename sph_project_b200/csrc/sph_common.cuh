@@ -93,6 +93,9 @@ struct Dev {
     // bricks (compact tiles of SPH_BRICK_X x Y x Z cells, one CTA each): flags set by the sort's gather, compacted list
     int* brick_flag;          // [nbricks] brick owns at least one fluid(-to-be) row
     int* brick_list;          // [nbricks] active brick ids, ascending
+    unsigned short* row_order;   // [cap] per brick, stored at the sorted indices of its owned rows in flat order: flat owned index of
+                                 // its k-th working row (fluid, owned by this rank), written by the list build
+    int* brick_nf;            // [nbricks] by position in brick_list: working rows in row_order, -1 = no row list
     int* brick_ctl;           // [0] active count  [1] ticket  [2] CTAs finished  [3] max window slots seen  [4] windows above the smem budget
     // per-sweep scalar payload of neighbour j, staged next to pv_j: (s0, s1, rho_j, m_j) with (s0, s1) =
     // (kappa, kappa / rho) for the DFSPH correction steps, (p / rho^2, p) for the pressure force
@@ -210,7 +213,7 @@ struct SphHandle {
     int ghost_stale = 0;
     bool rows_from_sort = false; // owned range was set by a slab sort (host edits must not widen it to the ghosts)
     int sticky_rc = 0;           // first error raised inside a void launcher (NCCL), reported by the caller
-    int wmax = 2304;             // shared-memory window budget (slots per brick) of the sweep kernels
+    int wmax = 2112;             // shared-memory window budget (slots per brick) of the sweep kernels
     int nbricks = 0;
     int solve_hint[2] = {2, 2};  // iterations the last DFSPH density / divergence solve took: size of the next first batch
     int solve_batch = 0;         // > 0: fixed number of solver iterations per host read (SPH_B200_BATCH_ITERS)

@@ -25,7 +25,7 @@ namespace {
 extern __shared__ __align__(16) float4 dyn_smem[];
 
 // resident CTAs per SM the register allocator has to make room for, by number of staged arrays (the window budget
-// of 2304 slots x 16 B x arrays allows 4 / 3 / 2 CTAs of 512 threads per SM)
+// of 2112 slots x 16 B x arrays allows 4 / 3 / 2 CTAs of 512 threads per SM)
 #ifndef SPH_BRICK_MINB1
 #define SPH_BRICK_MINB1 3
 #endif
@@ -47,21 +47,47 @@ __device__ __forceinline__ void add_wrench(const Dev& d, int obj, float3 force, 
     atomicAdd(w + 3, tq.x); atomicAdd(w + 4, tq.y); atomicAdd(w + 5, tq.z);
 }
 
-// Persistent CTA: draw bricks, stage the window of NARR arrays, call row(bk, r) for every owned row of the brick.
-template <int NARR, class RowFn>
-__device__ __forceinline__ void brick_for_rows(const Consts& c, const Dev& d, int wmax, bool stage, const float4* g0, const float4* g1,
-                                               const float4* g2, RowFn&& row) {
-    __shared__ BrickShared bsh;
-    Brick bk;
-    brick_init(bk, &bsh, dyn_smem, wmax, g0, g1, g2);
-    brick_first_tickets(d, bk);
-    while (brick_next(d, bk)) {
-        brick_open<NARR>(c, d, bk, wmax, stage);
+// Rows of the open brick.  With the build's compacted row list (sh.nf >= 0): warps draw groups of 32 consecutive
+// working rows from the brick's shared counter until none is left (no lanes parked on boundary particles, no warp
+// waiting while another one still has two groups to go); otherwise every owned row in flat order, one per thread and pass.
+template <class RowFn>
+__device__ __forceinline__ void brick_rows(const Consts& c, const Dev& d, const Brick& bk, RowFn&& row) {
+    BrickShared& sh = *bk.sh;
+    const int nf = sh.nf;
+    if (nf >= 0) {
+        const int lane = threadIdx.x & 31;
+        const int groups = (nf + 31) >> 5;
+        for (;;) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&sh.group, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= groups) break;
+            const int ts = g * 32 + lane;
+            if (ts < nf) {
+                const int t = d.row_order[brick_own_row(bk, ts).i];
+                row(bk, brick_own_row(bk, t));   // only working rows of this rank are in the order
+            }
+        }
+    } else {
         const int nown = brick_own_count(bk);
         for (int t = threadIdx.x; t < nown; t += SPH_BRICK_THREADS) {
             const BrickRow r = brick_own_row(bk, t);
             if (SPH_IS_ROW(c, r.i)) row(bk, r);
         }
+    }
+}
+
+// Persistent CTA: draw bricks, stage the window of NARR arrays, call row(bk, r) for every owned row of the brick.
+// lists: the neighbour lists (and with them the sorted row order) are valid.
+template <int NARR, class RowFn>
+__device__ __forceinline__ void brick_for_rows(const Consts& c, const Dev& d, int wmax, bool lists, const float4* g0, const float4* g1,
+                                               const float4* g2, RowFn&& row) {
+    __shared__ BrickSmem bsm;
+    Brick bk;
+    brick_begin(c, d, bk, &bsm, dyn_smem, wmax, g0, g1, g2, lists, lists);
+    while (brick_stage<NARR>(c, d, bk)) {
+        brick_rows(c, d, bk, row);
+        brick_advance(bk);
     }
 }
 
@@ -181,17 +207,82 @@ __device__ __forceinline__ void row_alpha(const Consts& c, const Dev& d, const B
     d.alpha[i] = sum_k > 1e-5f ? 1.0f / sum_k : 0.0f;
 }
 
-// BUILD: neighbour lists of every active brick; DENSITY / ALPHA: the two position-only sweeps that follow a sort,
-// on the window the build already staged.
+// BUILD: neighbour lists of every active brick and the compacted list of its working rows (fluid rows of this rank in
+// flat owned order: a stable compaction, so consecutive lanes stay spatial neighbours and share window slots);
+// DENSITY / ALPHA: the two position-only sweeps that follow a sort, on the window the build already staged.
 template <bool BUILD, bool DENSITY, bool ALPHA>
 __global__ void __launch_bounds__(SPH_BRICK_THREADS, SPH_BRICK_MINB1) kb_build(Consts c, Dev d, int wmax) {
-    brick_for_rows<1>(c, d, wmax, BUILD, d.pv, nullptr, nullptr, [&](const Brick& bk, BrickRow row) {
-        const float4 pi = brick_own_load(bk, row, 0);
-        if (!(pi.w > 0.0f)) return;
-        if (BUILD) brick_build_row(c, d, bk, row, pi);   // the thread reads back only what it wrote itself
-        if (DENSITY) row_density<BUILD, false>(c, d, bk, row.i, pi);
-        if (ALPHA) row_alpha<BUILD, false>(c, d, bk, row.i, pi);
-    });
+    __shared__ BrickSmem bsm;
+    __shared__ int s_warp[BRK_SORT_PASSES * BRK_WARPS + 1];   // working rows per (pass, warp), then exclusive offsets
+    Brick bk;
+    brick_begin(c, d, bk, &bsm, dyn_smem, wmax, d.pv, nullptr, nullptr, BUILD, false);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    while (brick_stage<1>(c, d, bk)) {
+        if (BUILD) {
+            const int nown = brick_own_count(bk);
+            const bool compactable = nown <= BRK_ROWS_MAX;
+            int rank[BRK_SORT_PASSES];
+            bool works[BRK_SORT_PASSES];
+            for (int t0 = 0; t0 < nown; t0 += BRK_ROWS_MAX) {   // one trip unless the brick is absurdly full
+#pragma unroll
+                for (int p = 0; p < BRK_SORT_PASSES; p++) {
+                    const int t = t0 + p * SPH_BRICK_THREADS + (int)threadIdx.x;
+                    bool w = false;
+                    if (t < nown) {
+                        const BrickRow row = brick_own_row(bk, t);
+                        if (SPH_IS_ROW(c, row.i)) {
+                            const float4 pi = brick_own_load(bk, row, 0);
+                            if (pi.w > 0.0f) {
+                                brick_build_row(c, d, bk, row, pi);
+                                w = true;
+                            }
+                        }
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, w);
+                    works[p] = w;
+                    rank[p] = __popc(m & ((1u << lane) - 1u));
+                    if (lane == 0) s_warp[p * BRK_WARPS + warp] = __popc(m);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {   // exclusive scan over (pass, warp): flat owned order
+                int carry = 0;
+#pragma unroll
+                for (int e0 = 0; e0 < BRK_SORT_PASSES * BRK_WARPS; e0 += 32) {
+                    const int e = e0 + lane;
+                    const int v = e < BRK_SORT_PASSES * BRK_WARPS ? s_warp[e] : 0;
+                    const int inc = brk_warp_inclusive_scan(v);
+                    if (e < BRK_SORT_PASSES * BRK_WARPS) s_warp[e] = carry + inc - v;
+                    carry += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (lane == 0) s_warp[BRK_SORT_PASSES * BRK_WARPS] = carry;
+            }
+            __syncthreads();
+            if (compactable) {
+#pragma unroll
+                for (int p = 0; p < BRK_SORT_PASSES; p++) {
+                    const int t = p * SPH_BRICK_THREADS + (int)threadIdx.x;
+                    // the brick's flat owned positions double as the storage of its row list: disjoint across bricks
+                    if (works[p]) d.row_order[brick_own_row(bk, s_warp[p * BRK_WARPS + warp] + rank[p]).i] = (unsigned short)t;
+                }
+            }
+            if (threadIdx.x == 0) {
+                const int nf = compactable ? s_warp[BRK_SORT_PASSES * BRK_WARPS] : -1;
+                d.brick_nf[bk.sh->ordinal] = nf;
+                bk.sh->nf = nf;
+            }
+            __syncthreads();   // lists and row list are visible to the whole CTA
+        }
+        if (DENSITY || ALPHA) {
+            brick_rows(c, d, bk, [&](const Brick& bk_, BrickRow row) {
+                const float4 pi = brick_own_load(bk_, row, 0);
+                if (!(pi.w > 0.0f)) return;
+                if (DENSITY) row_density<BUILD, false>(c, d, bk_, row.i, pi);
+                if (ALPHA) row_alpha<BUILD, false>(c, d, bk_, row.i, pi);
+            });
+        }
+        brick_advance(bk);
+    }
     brick_finish(d);
 }
 
