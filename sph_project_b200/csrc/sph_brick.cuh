@@ -387,30 +387,44 @@ __device__ __forceinline__ int brick_neighbors(const Consts& c, const Dev& d, co
                 int base = 0;
 #pragma unroll 1
                 for (;;) {
+                    if (ILP == 1) {
 #pragma unroll
-                    for (int u0 = 0; u0 < 16; u0 += ILP) {
-                        if (base + u0 > n) break;
-                        unsigned off[ILP];
-                        bool ok[ILP];
-                        float4 pj[ILP], aj[ILP], bj[ILP];
-#pragma unroll
-                        for (int k = 0; k < ILP; k++) {
-                            const int u = u0 + k;
-                            ok[k] = (u > 0 || base > 0) && base + u <= n;
-                            const unsigned o16 = (u & 1) ? ((w[u >> 1] >> 12) & 0xffff0u) : ((w[u >> 1] << 4) & 0xffff0u);   // 16 x slot
-                            off[k] = ok[k] ? o16 : 0u;
+                        for (int u = 0; u < 16; u++) {
+                            if ((u > 0 || base > 0) && base + u <= n) {
+                                const unsigned off = (u & 1) ? ((w[u >> 1] >> 12) & 0xffff0u) : ((w[u >> 1] << 4) & 0xffff0u);   // 16 x slot
+                                const float4 pj = lds128(a0 + off);
+                                const float4 aj = NARR > 1 ? (A_HALF ? lds64(a1 + off) : lds128(a1 + off)) : pj;
+                                const float4 bj = NARR > 2 ? lds128(a2 + off) : pj;
+                                const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+                                visit(NbrRef{(int)(off >> 4), true}, pj, aj, bj, R, dist2(R));
+                            }
                         }
+                    } else {
 #pragma unroll
-                        for (int k = 0; k < ILP; k++) {
-                            pj[k] = lds128(a0 + off[k]);
-                            aj[k] = NARR > 1 ? (A_HALF ? lds64(a1 + off[k]) : lds128(a1 + off[k])) : pj[k];
-                            bj[k] = NARR > 2 ? lds128(a2 + off[k]) : pj[k];
-                        }
-#pragma unroll
-                        for (int k = 0; k < ILP; k++) {
-                            if (ok[k]) {
-                                const float3 R = make_float3(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z);
-                                visit(NbrRef{(int)(off[k] >> 4), true}, pj[k], aj[k], bj[k], R, dist2(R));
+                        for (int u0 = 0; u0 < 16; u0 += ILP) {
+                            if (base + u0 > n) break;
+                            unsigned off[ILP];
+                            bool ok[ILP];
+                            float4 pj[ILP], aj[ILP], bj[ILP];
+    #pragma unroll
+                            for (int k = 0; k < ILP; k++) {
+                                const int u = u0 + k;
+                                ok[k] = (u > 0 || base > 0) && base + u <= n;
+                                const unsigned o16 = (u & 1) ? ((w[u >> 1] >> 12) & 0xffff0u) : ((w[u >> 1] << 4) & 0xffff0u);   // 16 x slot
+                                off[k] = ok[k] ? o16 : 0u;
+                            }
+    #pragma unroll
+                            for (int k = 0; k < ILP; k++) {
+                                pj[k] = lds128(a0 + off[k]);
+                                aj[k] = NARR > 1 ? (A_HALF ? lds64(a1 + off[k]) : lds128(a1 + off[k])) : pj[k];
+                                bj[k] = NARR > 2 ? lds128(a2 + off[k]) : pj[k];
+                            }
+    #pragma unroll
+                            for (int k = 0; k < ILP; k++) {
+                                if (ok[k]) {
+                                    const float3 R = make_float3(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z);
+                                    visit(NbrRef{(int)(off[k] >> 4), true}, pj[k], aj[k], bj[k], R, dist2(R));
+                                }
                             }
                         }
                     }

@@ -9,7 +9,9 @@ The host side is small on purpose:
                         same number of particles each (from a cell-layer histogram);
   * `broadcast_bytes`   ship the 128-byte NCCL unique id from rank 0 with torch.distributed
                         (works on the `nccl` and on the `gloo` backend);
-  * `SlabContext`       rank / world / ranges / ownership test used by the particle container.
+  * `SlabContext`       rank / world / ranges / ownership test used by the particle container;
+  * `slab_parity_check` the sharded run against the unsharded one on a small dam break (used by bench.py at N > 1 and
+                        by tests/slab_check.py): same particles, same positions, same solver iterations.
 """
 from __future__ import annotations
 
@@ -88,3 +90,82 @@ class SlabContext:
         c = np.asarray(layer_counts, dtype=np.int64)
         lo, hi = max(self.z_lo - 1, 0), min(self.z_hi + 1, self.nz)
         return int(c[lo:hi].sum() * slack) + extra
+
+
+def slab_parity_check(rank: int, world: int, local_rank: int, method: str = "dfsph", steps: int = 30) -> Optional[dict]:
+    """Every rank steps its slab of a small dam break; rank 0 also steps the same scene unsharded on its GPU and
+    compares positions / velocities by uid (north_star tolerance 1e-4 relative), solver iteration counts and particle
+    conservation.  Needs an initialised torch.distributed process group (one rank per GPU).  Returns the report on rank
+    0 (key "ok"), None elsewhere."""
+    import contextlib
+    import sys
+
+    import torch.distributed as dist
+
+    from .containers import DFSPHContainer, WCSPHContainer
+    from .fluid_solvers import DFSPHSolver, WCSPHSolver
+    from .utils import SimConfig
+
+    dt = 1e-3 if method == "dfsph" else 4e-4
+    scene = {
+        "Configuration": {
+            "domainStart": [0.0, 0.0, 0.0], "domainEnd": [0.6, 0.8, 0.4 * world + 0.4], "particleRadius": 0.01, "addDomainBox": True,
+            "density0": 1000.0, "gravitation": [0.0, -9.81, 0.0], "simulationMethod": method, "viscosityMethod": "standard",
+            "viscosity": 10.0, "viscosity_b": 5.0, "timeStepSize": dt, "exportFrame": False, "exportPly": False, "exportObj": False},
+        "FluidBlocks": [{"objectId": 0, "start": [0.1, 0.1, 0.1], "end": [0.3, 0.5, 0.4 * world + 0.3], "translation": [0, 0, 0],
+                         "scale": [1, 1, 1], "velocity": [0.0, -1.0, 0.3], "density": 1000.0, "color": [50, 100, 200], "entryTime": -1.0}]}
+    C, S = (DFSPHContainer, DFSPHSolver) if method == "dfsph" else (WCSPHContainer, WCSPHSolver)
+
+    def build(slab):
+        import copy
+        with contextlib.redirect_stdout(sys.stderr):
+            c = C(SimConfig(config=copy.deepcopy(scene), verbose=False), GGUI=False, device=local_rank, slab=slab)
+            s = S(c)
+            s.prepare()
+        return c, s
+
+    def run(s):
+        it = [0, 0]
+        for _ in range(steps):
+            st = s.step()
+            it[0] += st.total_dfsph_iterations
+            it[1] += st.total_dfsph_iterations_v
+        return it
+
+    c, s = build((rank, world))
+    it = run(s)
+    n = c.particle_num[None]
+    own = c.owned_mask()
+    payload = (c.particle_uids.to_numpy(n)[own], c.particle_positions.to_numpy(n)[own], c.particle_velocities.to_numpy(n)[own],
+               it, int(c.engine.slab_info().halo_calls))
+    gathered = [None] * world
+    dist.gather_object(payload, gathered if rank == 0 else None, dst=0)
+    del c, s
+    if rank != 0:
+        return None
+    cr, sr = build(None)
+    itr = run(sr)
+    nr = cr.particle_num[None]
+    uid_r = cr.particle_uids.to_numpy(nr)
+    xr = np.empty((nr, 3), np.float32)
+    xr[uid_r] = cr.particle_positions.to_numpy(nr)
+    vr = np.empty((nr, 3), np.float32)
+    vr[uid_r] = cr.particle_velocities.to_numpy(nr)
+    uid = np.concatenate([g[0] for g in gathered])
+    x = np.concatenate([g[1] for g in gathered])
+    v = np.concatenate([g[2] for g in gathered])
+    conserved = bool(uid.size == nr and np.array_equal(np.sort(uid), np.arange(nr)))
+    ex = ev = float("inf")
+    if conserved:
+        xs, vs = np.empty_like(xr), np.empty_like(vr)
+        xs[uid] = x
+        vs[uid] = v
+        ex = float(np.abs(xs - xr).max() / np.abs(xr).max())
+        ev = float(np.abs(vs - vr).max() / max(np.abs(vr).max(), 1e-6))
+    its = gathered[0][3]
+    same_it = abs(its[0] - itr[0]) <= 1 and abs(its[1] - itr[1]) <= 1
+    ok = bool(conserved and ex < 1e-4 and ev < 1e-2 and same_it)
+    return {"method": method, "world": world, "steps": steps, "particles": int(nr), "conserved": conserved,
+            "max_rel_position_error": ex, "max_rel_velocity_error": ev, "iterations_slab": [int(a) for a in its],
+            "iterations_single": [int(a) for a in itr], "owned_per_rank": [int(g[0].size) for g in gathered],
+            "halo_calls_rank0": gathered[0][4], "ok": ok}
