@@ -338,25 +338,29 @@ def solver_iterations(stats, steps):
             "pcisph": stats.total_pcisph_iterations / steps, "cg": stats.total_cg_iterations / steps}
 
 
-def fields_by_uid(container):
-    """(x, v) of the rank's owned particles ordered by uid (insertion index)."""
+def fields_by_uid(container, with_material=False):
+    """(x, v[, material]) of the rank's particles ordered by uid (insertion index)."""
     from sph_project_b200._native import F
     n = container.particle_num[None]
     uid = container.engine.get_field(F.UID, n)
-    x = container.engine.get_field(F.POSITION, n)
-    v = container.engine.get_field(F.VELOCITY, n)
-    xs, vs = np.empty_like(x), np.empty_like(v)
-    xs[uid] = x
-    vs[uid] = v
-    return xs, vs
+    out = []
+    for fid in (F.POSITION, F.VELOCITY) + ((F.MATERIAL,) if with_material else ()):
+        a = container.engine.get_field(fid, n)
+        b = np.empty_like(a)
+        b[uid] = a
+        out.append(b)
+    return tuple(out)
 
 
-def load_state(container, solver, xs, vs):
-    """Put a (x, v)-by-uid state into a freshly prepared simulation and redo what its step tail leaves behind
-    (sort, densities, DFSPH alpha: all functions of the positions)."""
+def load_state(container, solver, xs, vs, mat=None):
+    """Put a state by uid — positions, velocities and the materials (emitter particles are parked as rigid until they
+    cross gravitationUpper, base_solver.py:651-677) — into a freshly prepared simulation and redo what its step tail
+    leaves behind (sort, densities, DFSPH alpha: all functions of the positions)."""
     from sph_project_b200._native import F
     n = container.particle_num[None]
     uid = container.engine.get_field(F.UID, n)
+    if mat is not None:
+        container.engine.set_field(F.MATERIAL, mat[uid])
     container.engine.set_field(F.POSITION, xs[uid])
     container.engine.set_field(F.VELOCITY, vs[uid])
     container.prepare_neighborhood_search()
@@ -381,8 +385,8 @@ def make_state(args):
         raise SystemExit(3)
     c, s = make_sim(scene_for(args.config))
     c.engine.step(args.settle)
-    xs, vs = fields_by_uid(c)
-    np.savez(args.make_state, x=xs, v=vs, settle=args.settle)
+    xs, vs, mat = fields_by_uid(c, with_material=True)
+    np.savez(args.make_state, x=xs, v=vs, material=mat, settle=args.settle)
 
 
 def run_reference(args, rank, world):
@@ -402,7 +406,7 @@ def run_reference(args, rank, world):
         subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--make-state", state_path, "--config", args.config,
                         "--settle", str(args.settle)], check=True, stdout=sys.stderr, stderr=sys.stderr, timeout=900)
         st = np.load(state_path)
-        load_state(c, s, st["x"], st["v"])
+        load_state(c, s, st["x"], st["v"], st["material"])
         sample += f", the state the GPU library reaches after {args.settle} settle steps"
     except (subprocess.SubprocessError, OSError, KeyError, ValueError):
         window = "early"
@@ -567,19 +571,19 @@ def run_gpu(args, rank, world, local_rank):
     # ---- CPU baseline + parity at the benchmark state (rank 0, N=1): both step the SAME pressurised state ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        xs, vs = fields_by_uid(container)
+        xs, vs, mats = fields_by_uid(container, with_material=True)
         lib = oracle_library()
         c2, s2 = make_sim(scene_for(args.config), lib)
-        load_state(c2, s2, xs, vs)
-        load_state(container, solver, xs, vs)          # the GPU restarts from the very same host copy
+        load_state(c2, s2, xs, vs, mats)
+        load_state(container, solver, xs, vs, mats)    # the GPU restarts from the very same host copy
         t0 = time.perf_counter()
         one_it = solver_iterations(s2.step(1), 1)
         one = time.perf_counter() - t0
         k = int(min(max(round(12.0 / max(one, 1e-3)), 1), 20))      # about 12 s more of CPU work
         v, dt_cpu, st2 = time_cpu(s2, c2, k, 0)
         st_gpu = eng.step(1 + k)
-        xg, _ = fields_by_uid(container)
-        xo, _ = fields_by_uid(c2)
+        xg = fields_by_uid(container)[0]
+        xo = fields_by_uid(c2)[0]
         it_cpu = {key: val * k / (k + 1) + one_it[key] / (k + 1) for key, val in solver_iterations(st2, k).items()}
         cpu = {"value": v, "unit": UNIT, "cores": int(os.environ.get("OMP_NUM_THREADS", host_cores())), "kind": "port", "cpu": cpu_model(),
                "sample": f"full workload ({n_fluid} fluid + {n_total - n_fluid} boundary particles), {k} timed steps after 1 warm-up step from the "

@@ -328,6 +328,16 @@ int sph_slab_init(SphHandle* h, int32_t rank, int32_t world, const void* unique_
                   int64_t global_particle_num);
 int sph_slab_set_global_particle_num(SphHandle* h, int64_t n);
 int sph_slab_info(SphHandle* h, SphSlabInfo* out);
+/* Peer memory over NVLink / NVSwitch for the solver loops (optional; without it the loops use NCCL): every rank
+ * exports CUDA IPC handles of its velocity / payload arrays and of a small control block (sph_slab_peer_export,
+ * SPH_SLAB_PEER_BLOB_BYTES bytes), the host gathers the blobs (e.g. torch.distributed.all_gather_object) and hands
+ * every other rank's blob to sph_slab_peer_import.  Inside the DFSPH loops a rank then reads its ghosts' new
+ * velocities / kappa straight from the neighbour's arrays (one copy kernel behind a flag the neighbour's sweep sets
+ * in its epilogue) and the ranks exchange their error sums by storing them into each other's control blocks,
+ * instead of two ncclSend/ncclRecv pairs and one ncclAllReduce per iteration. */
+#define SPH_SLAB_PEER_BLOB_BYTES 512
+int sph_slab_peer_export(SphHandle* h, void* blob /*[SPH_SLAB_PEER_BLOB_BYTES]*/);
+int sph_slab_peer_import(SphHandle* h, int32_t peer_rank, const void* blob);
 
 #ifdef __cplusplus
 }

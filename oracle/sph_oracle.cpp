@@ -1361,5 +1361,7 @@ int sph_slab_unique_id(void*) { return SPH_E_UNSUPPORTED; }
 int sph_slab_init(SphHandle* h, int32_t, int32_t, const void*, int32_t, int32_t, int64_t) { return fail(h, SPH_E_UNSUPPORTED, "oracle holds the whole domain"); }
 int sph_slab_set_global_particle_num(SphHandle* h, int64_t) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
 int sph_slab_info(SphHandle* h, SphSlabInfo*) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
+int sph_slab_peer_export(SphHandle* h, void*) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
+int sph_slab_peer_import(SphHandle* h, int32_t, const void*) { return fail(h, SPH_E_UNSUPPORTED, "oracle"); }
 
 }  // extern "C"

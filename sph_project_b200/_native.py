@@ -20,6 +20,7 @@ METHOD_WCSPH, METHOD_PCISPH, METHOD_DFSPH = 0, 1, 2
 VISC_STANDARD, VISC_IMPLICIT = 0, 1
 MATERIAL_FLUID, MATERIAL_RIGID = 1, 2
 FLAG_SLAB = 1
+SLAB_PEER_BLOB_BYTES = 512
 
 
 class SphParams(C.Structure):
@@ -181,6 +182,8 @@ PROTOTYPES = {
     "sph_slab_init": (C.c_int, [_H, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
     "sph_slab_set_global_particle_num": (C.c_int, [_H, C.c_int64]),
     "sph_slab_info": (C.c_int, [_H, C.POINTER(SphSlabInfo)]),
+    "sph_slab_peer_export": (C.c_int, [_H, C.c_void_p]),
+    "sph_slab_peer_import": (C.c_int, [_H, C.c_int32, C.c_void_p]),
 }
 
 
@@ -410,6 +413,15 @@ class Engine:
 
     def slab_set_global_particle_num(self, n: int):
         self._check(self.lib.sph_slab_set_global_particle_num(self._h, int(n)))
+
+    def slab_peer_export(self) -> bytes:
+        buf = C.create_string_buffer(SLAB_PEER_BLOB_BYTES)
+        self._check(self.lib.sph_slab_peer_export(self._h, buf))
+        return buf.raw
+
+    def slab_peer_import(self, peer_rank: int, blob: bytes):
+        assert len(blob) == SLAB_PEER_BLOB_BYTES
+        self._check(self.lib.sph_slab_peer_import(self._h, int(peer_rank), C.create_string_buffer(blob, SLAB_PEER_BLOB_BYTES)))
 
     def slab_info(self) -> SphSlabInfo:
         info = SphSlabInfo()

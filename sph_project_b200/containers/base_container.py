@@ -162,6 +162,7 @@ class BaseContainer:
             uid = broadcast_bytes(uid, 128, src=0)
             self._engine.slab_init(self.slab.rank, self.slab.world, uid, self.slab.z_lo, self.slab.z_hi,
                                    self.global_particle_num)
+            self._connect_slab_peers()
 
         self.particle_num = ScalarField(eng, S.PARTICLE_NUM, int)
         self.fluid_particle_num = ScalarField(eng, S.FLUID_PARTICLE_NUM, int)
@@ -274,6 +275,27 @@ class BaseContainer:
         self._layer_counts = counts
         return SlabContext(rank=int(rank), world=int(world), dh=float(self.dh), nz=nz,
                            ranges=balanced_ranges(counts, int(world)))
+
+    def _connect_slab_peers(self):
+        """Exchange the CUDA IPC handles that let the solver loops read ghosts from the neighbours' memory over NVLink
+        (include/sph_b200.h, sph_slab_peer_*).  Optional: any failure leaves the NCCL path in place on every rank."""
+        import os
+        import torch.distributed as dist
+        ok, blob = 1, b""
+        if os.environ.get("SPH_B200_NO_PEER") == "1" or dist.get_backend() != "nccl":
+            ok = 0
+        else:
+            try:
+                blob = self._engine.slab_peer_export()
+            except nat.SphError:
+                ok = 0
+        blobs = [None] * self.slab.world
+        dist.all_gather_object(blobs, (ok, blob))
+        if not all(o for o, _ in blobs):
+            return
+        for r, (_, b) in enumerate(blobs):
+            if r != self.slab.rank:
+                self._engine.slab_peer_import(r, b)
 
     def owned_mask(self):
         """Live particles this rank owns (everything unless the container is a Z-slab: then not the ghosts)."""

@@ -176,24 +176,13 @@ int dfsph_solve(SphHandle* h, bool density, int* iters, float* err) {
     };
     int it = 0;
     float e = 0.f;
-    if (sph_is_slab(h)) {
-        // Z-slabs: the error sum crosses ranks (ncclAllReduce), so the test stays on the host, once per iteration
-        density_change(0, false);
-        while (it < 1 || it < 1000) {
-            correct(false);
-            if ((rc = zero_red(h, RED_ERR))) return rc;
-            density_change(1, false);
-            if ((rc = sph_slab_allreduce_red(h, RED_ERR, 1))) return rc;
-            if ((rc = read_red(h))) return rc;   // the reference's per-iteration device->host read
-            e = (float)h->h_red[RED_ERR] / global_particle_num(h);
-            it++;
-            if (e <= eta) break;
-        }
-        *iters = it; *err = e;
-        return last_launch(h);
-    }
+    // Z-slabs: the error sum crosses ranks, so an iteration is correction, density change (error sum only), all-reduce
+    // and the exit test as a one-thread kernel; every rank reads the same CTRL words and launches the same batches
+    const bool slab = sph_is_slab(h);
     if ((rc = zero_red(h, RED_ERR))) return rc;
     if ((rc = zero_red(h, CTRL_DONE, CTRL_COUNT))) return rc;
+    // with peer memory mapped, the ghost refreshes and the error sum of the loop go through the neighbours' memory
+    h->peer_loop = slab && sph_slab_peers_ready(h);
     density_change(0, false);
     int& hint = h->solve_hint[density ? 0 : 1];
     int launched = 0;
@@ -204,7 +193,13 @@ int dfsph_solve(SphHandle* h, bool density, int* iters, float* err) {
         if (batch > 1000 - launched) batch = 1000 - launched;
         for (int b = 0; b < batch; b++) {
             correct(true);
-            density_change(2, true);
+            if (!slab) {
+                density_change(2, true);
+            } else {
+                density_change(1, true);   // peer loop: the epilogue delivers the error sum to every rank
+                if (!h->peer_loop && (rc = sph_slab_allreduce_red(h, RED_ERR, 1))) { h->peer_loop = false; return rc; }
+                sph_launch_dfsph_solve_check(h, eta);
+            }
         }
         launched += batch;
         CUDA_TRY(h, cudaMemcpyAsync(h->h_red + CTRL_DONE, h->d.red + CTRL_DONE, sizeof(double) * CTRL_COUNT, cudaMemcpyDeviceToHost, h->stream));
@@ -212,6 +207,8 @@ int dfsph_solve(SphHandle* h, bool density, int* iters, float* err) {
         for (int k = 0; k < CTRL_COUNT; k++) ctrl[k] = h->h_red[CTRL_DONE + k];
         if (ctrl[0] != 0.0) break;
     }
+    h->peer_loop = false;
+    h->peer_signalled = 0;   // what is still stale after the loop is refreshed through NCCL
     it = (int)ctrl[CTRL_ITERS - CTRL_DONE];
     e = (float)ctrl[CTRL_ERR - CTRL_DONE];
     hint = it;

@@ -212,6 +212,8 @@ struct SphHandle {
     long long n_global = 0;
     int ghost_stale = 0;
     bool rows_from_sort = false; // owned range was set by a slab sort (host edits must not widen it to the ghosts)
+    bool peer_loop = false;      // inside a DFSPH solve whose halos / error sums go through peer memory (sph_slab.cu)
+    int peer_signalled = 0;      // ghost fields whose last writer signalled its completion to the peers
     int sticky_rc = 0;           // first error raised inside a void launcher (NCCL), reported by the caller
     int wmax = 2112;             // shared-memory window budget (slots per brick) of the sweep kernels
     int nbricks = 0;

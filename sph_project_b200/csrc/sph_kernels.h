@@ -39,6 +39,31 @@ __device__ __forceinline__ void block_reduce_add(double* dst, double v) {
 }
 #endif
 
+// ---- peer memory of the Z-slab solver loops (sph_slab.cu) -------------------------------------------------
+// One control block per rank in device memory, mapped into every other rank through CUDA IPC.  Counters only ever
+// grow; all ranks run the same kernels in the same order, so "the peer has signalled as often as I have" is the
+// whole handshake.
+#define SPH_PEER_MAX_RANKS 16
+struct PeerCtl {
+    int vel_count;                       // velocity writers (correction sweeps) this rank has completed
+    int aux_count;                       // payload writers (density-change sweeps)
+    int err_count;                       // error sums this rank has delivered to everybody
+    int pad0;
+    int layout[4];                       // own_begin, own_end, send_lo_n, send_hi_n after the last sort
+    int err_flag[SPH_PEER_MAX_RANKS];    // written by rank q: error sums q has delivered into THIS block
+    double partial[2][SPH_PEER_MAX_RANKS];   // [delivery parity][rank q]: q's error sum
+};
+// what a sweep needs to signal / deliver in its epilogue (all null / 0 outside peer loops)
+struct PeerLinks {
+    PeerCtl* mine;
+    PeerCtl* const* all;                 // device array [world] of every rank's block (own included)
+    int world, rank;
+};
+bool sph_slab_peers_ready(const SphHandle* h);
+PeerLinks sph_slab_peer_links(const SphHandle* h);
+void sph_slab_peer_pull(SphHandle* h, int which /* GHOST_VEL | GHOST_AUX */, bool speculative);
+void sph_slab_publish_layout(SphHandle* h);
+
 // sph_slab.cu
 enum GhostField { GHOST_VEL = 1, GHOST_AUX = 2, GHOST_RHO = 4, GHOST_PV = 8 };
 bool sph_is_slab(const SphHandle* h);
@@ -48,7 +73,11 @@ int sph_slab_halo(SphHandle* h, void* base, int elem_bytes);
 int sph_slab_allreduce_red(SphHandle* h, int slot, int count);
 void sph_slab_free(SphHandle* h);
 // mark / refresh ghost copies (no-ops unless the handle is a slab)
-inline void sph_ghost_dirty(SphHandle* h, int what) { if (h->slab) h->ghost_stale |= what; }
+inline void sph_ghost_dirty(SphHandle* h, int what) {
+    if (!h->slab) return;
+    h->ghost_stale |= what;
+    h->peer_signalled &= ~what;   // a writer that does not signal: the next refresh goes through NCCL (peer-loop launchers set the bit afterwards)
+}
 void sph_ghost_sync(SphHandle* h, int what);
 
 // sph_grid.cu
@@ -69,6 +98,7 @@ void sph_launch_dfsph_alpha(SphHandle* h);
 void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused, int mode = 0, bool speculative = false, float eta = 0.0f);
 void sph_launch_dfsph_density_star(SphHandle* h, bool fused, int mode = 0, bool speculative = false, float eta = 0.0f);
 bool sph_lists_ready(SphHandle* h);
+void sph_launch_dfsph_solve_check(SphHandle* h, float eta);   // Z-slabs: the exit test after the all-reduce of the error sum
 void sph_launch_dfsph_correct_divergence(SphHandle* h, bool aux_ready, bool speculative = false);   // aux_ready: fused kernel wrote kappa into aux
 void sph_launch_dfsph_correct_density(SphHandle* h, bool aux_ready, bool speculative = false);
 void sph_launch_pcisph_density_star(SphHandle* h);

@@ -90,6 +90,16 @@ struct SlabState {
     int* d_counts = nullptr;              // [0..1] send counts lo/hi, [2..3] recv counts lo/hi
     int* h_ints = nullptr;                // pinned
     int64_t halo_bytes = 0, halo_calls = 0;
+    // peer memory (CUDA IPC over NVLink), optional
+    PeerCtl* ctl = nullptr;                          // my control block (device)
+    PeerCtl* peer_ctl[SPH_PEER_MAX_RANKS] = {nullptr};   // every rank's block as mapped here (own included)
+    PeerCtl** d_peer_ctl = nullptr;                  // the same table in device memory
+    float4* peer_vm[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [side lo / hi][exporter's vm / vm_alt]
+    float4* peer_aux[2] = {nullptr, nullptr};
+    float4* export_vm = nullptr;                     // my d.vm at export time (tells which half is current later)
+    int imported = 0;
+    bool peers_ready = false;
+    int64_t peer_pulls = 0;
 };
 
 namespace {
@@ -285,6 +295,7 @@ int sph_slab_post_scan(SphHandle* h) {
     c.row_begin = s->own_begin;
     c.row_end = s->own_end;
     h->rows_from_sort = true;
+    sph_slab_publish_layout(h);
     return SPH_OK;
 }
 
@@ -316,9 +327,108 @@ int sph_slab_allreduce_red(SphHandle* h, int slot, int count) {
     return SPH_OK;
 }
 
+
+// ---- peer memory ------------------------------------------------------------------------------------------
+namespace {
+
+struct PeerBlob {
+    int magic, rank;
+    cudaIpcMemHandle_t vm, vm_alt, aux, ctl;
+};
+static_assert(sizeof(PeerBlob) <= SPH_SLAB_PEER_BLOB_BYTES, "blob size");
+constexpr int PEER_MAGIC = 0x53504831;
+
+__device__ __forceinline__ int ld_volatile_i32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_volatile_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// Ghost refresh straight from the neighbours' arrays: blockIdx.y = side (0: lower neighbour, 1: upper).  Waits until
+// the neighbour has completed as many writers of this field as this rank has (its sweep's epilogue counts them), then
+// copies the neighbour's boundary layer — same particles, same order as my ghost layer — over NVLink.
+__global__ void __launch_bounds__(256) k_peer_pull(float4* mine_arr, const float4* peer_lo_arr, const float4* peer_hi_arr,
+                                                   const PeerCtl* ctl, const PeerCtl* peer_lo, const PeerCtl* peer_hi, int which_aux,
+                                                   int ghost_lo_begin, int ghost_lo_n, int ghost_hi_begin, int ghost_hi_n,
+                                                   const double* red, int speculative) {
+    if (speculative && red[CTRL_DONE] != 0.0) return;   // the writers returned early as well: nothing was signalled
+    const int side = blockIdx.y;
+    const PeerCtl* peer = side == 0 ? peer_lo : peer_hi;
+    const int n = side == 0 ? ghost_lo_n : ghost_hi_n;
+    if (!peer || n <= 0) return;
+    if (threadIdx.x == 0) {
+        const int want = which_aux ? ctl->aux_count : ctl->vel_count;
+        const int* flag = which_aux ? &peer->aux_count : &peer->vel_count;
+        while (ld_volatile_i32(flag) < want) __nanosleep(64);
+        __threadfence_system();
+    }
+    __syncthreads();
+    // my lower ghost layer is the lower neighbour's TOP boundary layer, my upper one the upper neighbour's BOTTOM layer
+    const int src0 = side == 0 ? ld_volatile_i32(&peer->layout[1]) - n : ld_volatile_i32(&peer->layout[0]);
+    const int dst0 = side == 0 ? ghost_lo_begin : ghost_hi_begin;
+    const float4* src = side == 0 ? peer_lo_arr : peer_hi_arr;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) mine_arr[dst0 + k] = ld_volatile_f4(src + src0 + k);
+}
+
+}  // namespace
+
+bool sph_slab_peers_ready(const SphHandle* h) { return h->slab && h->slab->peers_ready; }
+
+PeerLinks sph_slab_peer_links(const SphHandle* h) {
+    PeerLinks l;
+    l.mine = nullptr; l.all = nullptr; l.world = 0; l.rank = 0;
+    if (sph_slab_peers_ready(h) && h->peer_loop) {
+        l.mine = h->slab->ctl;
+        l.all = h->slab->d_peer_ctl;
+        l.world = h->slab->world;
+        l.rank = h->slab->rank;
+    }
+    return l;
+}
+
+// the index ranges the neighbours need to address my boundary layers (stream-ordered behind the sort)
+void sph_slab_publish_layout(SphHandle* h) {
+    SlabState* s = h->slab;
+    if (!s || !s->ctl) return;
+    int* v = s->h_ints + 24;
+    v[0] = s->own_begin; v[1] = s->own_end; v[2] = s->send_lo_n; v[3] = s->send_hi_n;
+    cudaMemcpyAsync(s->ctl->layout, v, 4 * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+}
+
+void sph_slab_peer_pull(SphHandle* h, int which, bool speculative) {
+    SlabState* s = h->slab;
+    const bool aux = which == GHOST_AUX;
+    const int lo = s->rank - 1, hi = s->rank + 1;
+    // which half of the neighbours' velocity ping-pong is current: every rank has swapped as often as this one
+    const int half = (h->d.vm == s->export_vm) ? 0 : 1;
+    const float4* src_lo = lo >= 0 ? (aux ? s->peer_aux[0] : s->peer_vm[0][half]) : nullptr;
+    const float4* src_hi = hi < s->world ? (aux ? s->peer_aux[1] : s->peer_vm[1][half]) : nullptr;
+    const int nmax = s->ghost_lo_n > s->ghost_hi_n ? s->ghost_lo_n : s->ghost_hi_n;
+    if (nmax <= 0) return;
+    int gx = (nmax + 255) / 256;
+    if (gx > 64) gx = 64;
+    SphProf _prof(h, "k_peer_pull");
+    k_peer_pull<<<dim3(gx, 2), 256, 0, h->stream>>>(aux ? h->d.aux : h->d.vm, src_lo, src_hi, s->ctl, lo >= 0 ? s->peer_ctl[lo] : nullptr,
+                                                     hi < s->world ? s->peer_ctl[hi] : nullptr, aux ? 1 : 0, s->own_begin - s->ghost_lo_n,
+                                                     s->ghost_lo_n, s->own_end, s->ghost_hi_n, h->d.red, speculative ? 1 : 0);
+    h->launches++;
+    s->peer_pulls++;
+}
+
 void sph_slab_free(SphHandle* h) {
     SlabState* s = h->slab;
     if (!s) return;
+    for (int r = 0; r < SPH_PEER_MAX_RANKS; r++)
+        if (s->peer_ctl[r] && s->peer_ctl[r] != s->ctl) cudaIpcCloseMemHandle(s->peer_ctl[r]);
+    for (int side = 0; side < 2; side++) {
+        for (int k = 0; k < 2; k++) if (s->peer_vm[side][k]) cudaIpcCloseMemHandle(s->peer_vm[side][k]);
+        if (s->peer_aux[side]) cudaIpcCloseMemHandle(s->peer_aux[side]);
+    }
     if (s->comm && g_nccl.ok) g_nccl.CommDestroy(s->comm);
     if (s->h_ints) cudaFreeHost(s->h_ints);
     delete s;
@@ -384,6 +494,65 @@ int sph_slab_info(SphHandle* h, SphSlabInfo* out) {
     out->n_send_lo = s->send_lo_n; out->n_send_hi = s->send_hi_n;
     out->own_begin = s->own_begin; out->own_end = s->own_end;
     out->halo_bytes = s->halo_bytes; out->halo_calls = s->halo_calls;
+    return SPH_OK;
+}
+
+int sph_slab_peer_export(SphHandle* h, void* blob) {
+    if (!h || !blob) return SPH_E_INVALID;
+    if (!h->slab) return fail(h, SPH_E_STATE, "not a slab handle");
+    SlabState* s = h->slab;
+    if (s->world > SPH_PEER_MAX_RANKS) return fail(h, SPH_E_UNSUPPORTED, "too many ranks for the peer control block");
+    cudaSetDevice(h->P.device);
+    if (!s->ctl) {
+        void* p = nullptr;
+        CU_TRY(h, cudaMalloc(&p, sizeof(PeerCtl)));
+        h->allocations.push_back(p);
+        s->ctl = (PeerCtl*)p;
+        CU_TRY(h, cudaMemset(p, 0, sizeof(PeerCtl)));
+        CU_TRY(h, cudaMalloc(&p, sizeof(PeerCtl*) * SPH_PEER_MAX_RANKS));
+        h->allocations.push_back(p);
+        s->d_peer_ctl = (PeerCtl**)p;
+    }
+    PeerBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = PEER_MAGIC;
+    b.rank = s->rank;
+    CU_TRY(h, cudaIpcGetMemHandle(&b.vm, h->d.vm));
+    CU_TRY(h, cudaIpcGetMemHandle(&b.vm_alt, h->d.vm_alt));
+    CU_TRY(h, cudaIpcGetMemHandle(&b.aux, h->d.aux));
+    CU_TRY(h, cudaIpcGetMemHandle(&b.ctl, s->ctl));
+    s->export_vm = h->d.vm;
+    memset(blob, 0, SPH_SLAB_PEER_BLOB_BYTES);
+    memcpy(blob, &b, sizeof b);
+    return SPH_OK;
+}
+
+int sph_slab_peer_import(SphHandle* h, int32_t peer_rank, const void* blob) {
+    if (!h || !blob) return SPH_E_INVALID;
+    if (!h->slab || !h->slab->ctl) return fail(h, SPH_E_STATE, "export this rank's handles first");
+    SlabState* s = h->slab;
+    PeerBlob b;
+    memcpy(&b, blob, sizeof b);
+    if (b.magic != PEER_MAGIC || b.rank != peer_rank || peer_rank < 0 || peer_rank >= s->world || peer_rank == s->rank)
+        return fail(h, SPH_E_INVALID, "bad peer blob");
+    cudaSetDevice(h->P.device);
+    void* p = nullptr;
+    CU_TRY(h, cudaIpcOpenMemHandle(&p, b.ctl, cudaIpcMemLazyEnablePeerAccess));
+    s->peer_ctl[peer_rank] = (PeerCtl*)p;
+    const int side = peer_rank == s->rank - 1 ? 0 : (peer_rank == s->rank + 1 ? 1 : -1);
+    if (side >= 0) {
+        CU_TRY(h, cudaIpcOpenMemHandle(&p, b.vm, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_vm[side][0] = (float4*)p;
+        CU_TRY(h, cudaIpcOpenMemHandle(&p, b.vm_alt, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_vm[side][1] = (float4*)p;
+        CU_TRY(h, cudaIpcOpenMemHandle(&p, b.aux, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_aux[side] = (float4*)p;
+    }
+    if (++s->imported == s->world - 1) {
+        s->peer_ctl[s->rank] = s->ctl;
+        CU_TRY(h, cudaMemcpy(s->d_peer_ctl, s->peer_ctl, sizeof(PeerCtl*) * SPH_PEER_MAX_RANKS, cudaMemcpyHostToDevice));
+        s->peers_ready = true;
+    }
     return SPH_OK;
 }
 

@@ -407,7 +407,27 @@ struct SolveCtl {
     int speculative;   // launched ahead of the exit test: return at once when red[CTRL_DONE] is set
     float n_global;    // particle_num of the whole domain (the reference averages over fluid AND boundary rows)
     float eta;
+    PeerLinks peer;    // Z-slab peer loops: whom to tell that this sweep is complete / where the error sum goes
 };
+
+// Epilogue of a sweep inside a peer loop (thread 0 of the last CTA to finish; every write of the grid is visible here):
+// count the completed writer where the neighbours' ghost pulls look for it.
+__device__ __forceinline__ void peer_signal(const PeerLinks& p, bool aux) {
+    if (!p.mine) return;
+    __threadfence_system();
+    int* cnt = aux ? &p.mine->aux_count : &p.mine->vel_count;
+    *(volatile int*)cnt = *(volatile int*)cnt + 1;
+}
+// ... and deliver this rank's error sum into every rank's control block (own included), then clear it
+__device__ __forceinline__ void peer_deliver_error(const PeerLinks& p, double* red_err) {
+    const double part = *(volatile double*)red_err;
+    const int count = *(volatile int*)&p.mine->err_count + 1;
+    for (int q = 0; q < p.world; q++) *(volatile double*)&p.all[q]->partial[count & 1][p.rank] = part;
+    __threadfence_system();
+    for (int q = 0; q < p.world; q++) *(volatile int*)&p.all[q]->err_flag[p.rank] = count;
+    *(volatile int*)&p.mine->err_count = count;
+    *red_err = 0.0;
+}
 
 // DFSPH compute_density_derivative (DFSPH.py:65-101) / compute_density_star (:104-126).
 // FUSED (the library's own solver loops): also the kappa of the next correction step
@@ -445,6 +465,10 @@ __global__ void __launch_bounds__(SPH_BRICK_THREADS, SPH_BRICK_MINB2) kb_dfsph_d
     });
     if (FUSED && ctl.mode != SOLVE_PLAIN) block_reduce_add(d.red + RED_ERR, (double)err);
     const bool last = brick_finish(d);
+    if (FUSED && last) {
+        peer_signal(ctl.peer, true);   // aux (kappa) of my boundary layers is final
+        if (ctl.peer.mine && ctl.mode == SOLVE_SUM) peer_deliver_error(ctl.peer, d.red + RED_ERR);
+    }
     if (FUSED && ctl.mode == SOLVE_TEST && last) {
         // host arithmetic: f32 division of the f64 sum by the particle count, compare with eta
         const float e = (float)(*(volatile double*)(d.red + RED_ERR)) / ctl.n_global;
@@ -453,6 +477,29 @@ __global__ void __launch_bounds__(SPH_BRICK_THREADS, SPH_BRICK_MINB2) kb_dfsph_d
         if (e <= ctl.eta) d.red[CTRL_DONE] = 1.0;
         d.red[RED_ERR] = 0.0;
     }
+}
+
+// The same loop-exit test as a kernel of its own, for Z-slabs: red[RED_ERR] has just been summed over the ranks by the
+// all-reduce, so every rank takes the same decision from the same number.
+__global__ void k_dfsph_solve_check(Dev d, SolveCtl ctl) {
+    if (d.red[CTRL_DONE] == 0.0) {
+        if (ctl.peer.mine) {   // peer loop: wait for every rank's delivery of this round, sum in rank order
+            const PeerCtl* me = ctl.peer.mine;
+            const int want = *(volatile const int*)&me->err_count;
+            double sum = 0.0;
+            for (int q = 0; q < ctl.peer.world; q++) {
+                while (*(volatile const int*)&me->err_flag[q] < want) __nanosleep(64);
+            }
+            __threadfence_system();
+            for (int q = 0; q < ctl.peer.world; q++) sum += *(volatile const double*)&me->partial[want & 1][q];
+            d.red[RED_ERR] = sum;
+        }
+        const float e = (float)d.red[RED_ERR] / ctl.n_global;
+        d.red[CTRL_ITERS] += 1.0;
+        d.red[CTRL_ERR] = (double)e;
+        if (e <= ctl.eta) d.red[CTRL_DONE] = 1.0;
+    }
+    d.red[RED_ERR] = 0.0;
 }
 
 // DFSPH correct_divergence_step (DFSPH.py:161-202) / correct_density_error_step (:245-283).
@@ -488,7 +535,7 @@ __global__ void __launch_bounds__(SPH_BRICK_THREADS, SPH_BRICK_MINB2) kb_dfsph_c
         float4 v = d.vm[i];
         d.vm[i] = make_float4(v.x + dv.x, v.y + dv.y, v.z + dv.z, v.w);
     });
-    brick_finish(d);
+    if (brick_finish(d)) peer_signal(ctl.peer, false);   // velocities of my boundary layers are final
 }
 
 // PCISPH compute_density_star (PCISPH.py:32-62): predicted positions, no self term, neighbour
@@ -664,10 +711,18 @@ void sph_ghost_sync(SphHandle* h, int what) {
     int rc = 0;
     if (!rc && (need & GHOST_PV)) rc = sph_slab_halo(h, h->d.pv, 16);
     if (!rc && (need & GHOST_RHO)) rc = sph_slab_halo(h, h->d.rho, 4);
-    if (!rc && (need & GHOST_VEL)) rc = sph_slab_halo(h, h->d.vm, 16);
-    if (!rc && (need & GHOST_AUX)) rc = sph_slab_halo(h, h->d.aux, 16);
+    // inside a peer loop the writers have signalled their completion: pull the ghosts from the neighbours' memory
+    if (!rc && (need & GHOST_VEL)) {
+        if (h->peer_signalled & GHOST_VEL) sph_slab_peer_pull(h, GHOST_VEL, true);
+        else rc = sph_slab_halo(h, h->d.vm, 16);
+    }
+    if (!rc && (need & GHOST_AUX)) {
+        if (h->peer_signalled & GHOST_AUX) sph_slab_peer_pull(h, GHOST_AUX, true);
+        else rc = sph_slab_halo(h, h->d.aux, 16);
+    }
     if (rc && !h->sticky_rc) h->sticky_rc = rc;
     h->ghost_stale &= ~need;
+    h->peer_signalled &= ~need;
 }
 
 static void prep_aux(SphHandle* h, int mode) {
@@ -740,6 +795,7 @@ static SolveCtl solve_ctl(SphHandle* h, int mode, bool speculative, float eta) {
     ctl.speculative = speculative ? 1 : 0;
     ctl.n_global = h->slab ? (float)h->n_global : (float)h->c.N;
     ctl.eta = eta;
+    ctl.peer = sph_slab_peer_links(h);
     return ctl;
 }
 
@@ -747,7 +803,10 @@ static SolveCtl solve_ctl(SphHandle* h, int mode, bool speculative, float eta) {
 template <bool STAR>
 static void launch_density_change(SphHandle* h, bool fused, int mode, bool speculative, float eta) {
     sph_ghost_sync(h, GHOST_PV | (STAR ? GHOST_RHO : 0) | GHOST_VEL);
-    if (fused) sph_ghost_dirty(h, GHOST_AUX);
+    if (fused) {
+        sph_ghost_dirty(h, GHOST_AUX);
+        if (h->peer_loop) h->peer_signalled |= GHOST_AUX; else h->peer_signalled &= ~GHOST_AUX;
+    }
     const SolveCtl ctl = solve_ctl(h, fused ? mode : SOLVE_PLAIN, speculative, eta);
     if (sph_lists_ready(h)) {
         if (fused) LAUNCH_BRICK(2, (kb_dfsph_density_change<STAR, true, true>), ctl);
@@ -756,6 +815,11 @@ static void launch_density_change(SphHandle* h, bool fused, int mode, bool specu
         if (fused) LAUNCH_BRICK(2, (kb_dfsph_density_change<STAR, false, true>), ctl);
         else LAUNCH_BRICK(2, (kb_dfsph_density_change<STAR, false, false>), ctl);
     }
+}
+void sph_launch_dfsph_solve_check(SphHandle* h, float eta) {
+    SphProf _prof(h, "k_dfsph_solve_check");
+    k_dfsph_solve_check<<<1, 1, 0, h->stream>>>(h->d, solve_ctl(h, SOLVE_TEST, true, eta));
+    h->launches++;
 }
 void sph_launch_dfsph_density_derivative(SphHandle* h, bool fused, int mode, bool speculative, float eta) {
     launch_density_change<false>(h, fused, mode, speculative, eta);
@@ -773,6 +837,7 @@ static void launch_correct(SphHandle* h, int aux_mode, bool speculative) {
     if (sph_lists_ready(h)) { if (wrench) LAUNCH_BRICK(2, (kb_dfsph_correct<true, true>), ctl); else LAUNCH_BRICK(2, (kb_dfsph_correct<true, false>), ctl); }
     else { if (wrench) LAUNCH_BRICK(2, (kb_dfsph_correct<false, true>), ctl); else LAUNCH_BRICK(2, (kb_dfsph_correct<false, false>), ctl); }
     sph_ghost_dirty(h, GHOST_VEL);
+    if (h->peer_loop) h->peer_signalled |= GHOST_VEL; else h->peer_signalled &= ~GHOST_VEL;
 }
 void sph_launch_dfsph_correct_divergence(SphHandle* h, bool aux_ready, bool speculative) { launch_correct(h, aux_ready ? -1 : AUX_KAPPA_V, speculative); }
 void sph_launch_dfsph_correct_density(SphHandle* h, bool aux_ready, bool speculative) { launch_correct(h, aux_ready ? -1 : AUX_KAPPA, speculative); }

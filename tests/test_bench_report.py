@@ -106,11 +106,11 @@ def test_state_transfer_reproduces_the_run():
     lib = oracle_library()
     ca, sa = bench.make_sim(sc, lib)
     sa.step(5)
-    xs, vs = bench.fields_by_uid(ca)
+    xs, vs, mats = bench.fields_by_uid(ca, with_material=True)
     cb, sb = bench.make_sim(sc, lib)
-    bench.load_state(cb, sb, xs, vs)
+    bench.load_state(cb, sb, xs, vs, mats)
     ia, ib = sa.step(3), sb.step(3)
-    xa, _ = bench.fields_by_uid(ca)
-    xb, _ = bench.fields_by_uid(cb)
+    xa = bench.fields_by_uid(ca)[0]
+    xb = bench.fields_by_uid(cb)[0]
     assert ia.total_dfsph_iterations == ib.total_dfsph_iterations
     assert np.abs(xa - xb).max() / np.abs(xa).max() < 1e-6
