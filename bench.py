@@ -10,6 +10,8 @@ Workloads (`--config`, BASELINE.json `configs`; geometry in data/scenes/*.json):
   c2_wcsph     the same geometry under WCSPH, dt = 4e-4
   c3_bath      DFSPH bath, 321,750 fluid + 216,279 boundary particles, dt = 2e-3 (dragon_bath without its mesh bodies)
   c4_buckling  PCISPH + implicit viscosity sheet, 106,400 fluid + 2,065,095 boundary particles, dt = 1e-3
+  c5_dam10m    BASELINE's 8-GPU scene: 10,000,000 fluid + 957,279 boundary particles in a 6 x 6 x 8 m tank, DFSPH, the
+               same scene cut into N Z-slabs (strong scaling; meant for --gpus 8, fits from 2 GPUs up)
 The lattices start 20 % under-dense, so a run first pre-rolls `--settle` untimed steps into the pressurised regime
 (BASELINE.md "W-pressurised"), then W warm-up steps, then times exactly K steps between two CUDA events on the stream
 the library launches on.
@@ -51,6 +53,8 @@ CONFIGS = {
     "c3_bath": ("bath_500k_dfsph.json", "fluid particle-steps/s (DFSPH bath)", 300, "DFSPH bath, dragon_bath geometry without mesh bodies, dt=2e-3"),
     "c4_buckling": ("buckling_pcisph_implicit.json", "fluid particle-steps/s (PCISPH + implicit viscosity)", 50,
                     "PCISPH + implicit-viscosity sheet, final_scene3 geometry without the mesh body, dt=1e-3"),
+    "c5_dam10m": ("dam_break_10m_dfsph.json", "fluid particle-steps/s (DFSPH 10M dam-break)", 300,
+                  "DFSPH dam-break, 6 x 6 x 8 m tank, 10 M fluid particles, dt=6e-4 (BASELINE config 5; Z-slabs over the GPUs of one box, strong scaling)"),
 }
 
 # compulsory bytes per particle per launch (each needed field read once, each result written once);
@@ -327,7 +331,7 @@ def static_config(name, n_gpus, settle, n_fluid, n_total, grid):
     """The `config` object: what the workload is, identical in both arms (what was measured goes elsewhere)."""
     what = CONFIGS[name][3]
     return {"workload": f"{name}: {what}; {n_fluid} fluid + {n_total - n_fluid} boundary particles"
-                        + (f" ({n_gpus} Z-slabs of ~1.23 M fluid particles each, weak scaling)" if n_gpus > 1 else ""),
+                        + ((f" ({n_gpus} Z-slabs of ~1.23 M fluid particles each, weak scaling)" if name != "c5_dam10m" else f" ({n_gpus} Z-slabs of one scene)") if n_gpus > 1 else ""),
             "n_fluid": n_fluid, "n_total": n_total, "grid": grid,
             "window": f"W-pressurised: state after {settle} settle steps from the initial lattice, then warm-up and timed steps",
             "l2": "per-step working set ~0.5 GB > 126 MB L2: no flush needed", "parallelism": f"zslab{n_gpus}"}
@@ -396,14 +400,16 @@ def run_reference(args, rank, world):
     lib = oracle_library()
     cores = int(os.environ.get("OMP_NUM_THREADS", host_cores()))   # the OpenMP team size actually used
     t0 = time.perf_counter()
-    sc = scene_for(args.config)
+    # the 10 M-particle scene is sampled by the 1.23 M dam break (same solver, spacing and tank depth per slab)
+    sample_config = "c2p_dfsph" if args.config == "c5_dam10m" else args.config
+    sc = scene_for(sample_config)
     c, s = make_sim(sc, lib)
     n_fluid, n_total = int(c.fluid_particle_num[None]), int(c.particle_num[None])
-    sample = f"full 1-GPU workload ({n_fluid} fluid + {n_total - n_fluid} boundary particles)"
+    sample = f"{'full 1-GPU workload' if sample_config == args.config else 'bounded sample: the c2p_dfsph dam break'} ({n_fluid} fluid + {n_total - n_fluid} boundary particles)"
     window = "pressurised"
     state_path = os.path.join(tempfile.gettempdir(), f"sph_b200_state_{args.config}_{args.settle}_{os.getpid()}.npz")
     try:   # the pre-roll is the GPU library's (untimed, in a child process); the timed steps below are pure oracle
-        subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--make-state", state_path, "--config", args.config,
+        subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--make-state", state_path, "--config", sample_config,
                         "--settle", str(args.settle)], check=True, stdout=sys.stderr, stderr=sys.stderr, timeout=900)
         st = np.load(state_path)
         load_state(c, s, st["x"], st["v"], st["material"])
@@ -446,8 +452,8 @@ def run_gpu(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        if args.config not in ("c2p_dfsph", "c2_wcsph"):
-            raise SystemExit("Z-slab weak scaling is defined for the dam-break configs (c2p_dfsph, c2_wcsph)")
+        if args.config not in ("c2p_dfsph", "c2_wcsph", "c5_dam10m"):
+            raise SystemExit("Z-slabs are defined for the dam-break configs (c2p_dfsph, c2_wcsph: weak scaling; c5_dam10m: one scene)")
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -459,7 +465,7 @@ def run_gpu(args, rank, world, local_rank):
     slab_parity = None
     if world > 1:
         from sph_project_b200.slab import slab_parity_check
-        slab_parity = slab_parity_check(rank, world, local_rank, method="dfsph" if args.config == "c2p_dfsph" else "wcsph", steps=30)
+        slab_parity = slab_parity_check(rank, world, local_rank, method="wcsph" if args.config == "c2_wcsph" else "dfsph", steps=30)
 
     t_setup = time.perf_counter()
     # N > 1: weak scaling, the domain and the block grow along z by one 1.23M-particle slab per GPU
@@ -594,7 +600,7 @@ def run_gpu(args, rank, world, local_rank):
     if rank == 0:
         line = {
             "metric": CONFIGS[args.config][1], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.config == "c5_dam10m" else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": static_config(args.config, world, args.settle, *workload_numbers(args.config, n_slabs=world)),
             "stats": {"mean_iterations": solver_iterations(stats, args.steps), "window": "pressurised",

@@ -29,6 +29,7 @@
 #pragma once
 
 #include "sph_common.cuh"
+#include "sph_kernels.h"
 
 #ifndef SPH_BRICK_X
 #define SPH_BRICK_X 4
@@ -118,6 +119,20 @@ __device__ __forceinline__ float4 lds64(unsigned addr) {   // first two componen
     return v;
 }
 
+__device__ __forceinline__ int brk_ld_volatile_i32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 brk_ld_volatile_f4(const float4* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts128(unsigned addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ---- per-CTA brick state in shared memory -----------------------------------------------------------
 // Tables of one brick.  Two sets per CTA: while the CTA works on one brick, warp 0 prepares the tables of the next,
 // so a single barrier and the TMA round trip are all that separates two bricks.
@@ -131,10 +146,22 @@ struct BrickShared {
     int group;                   // next group of 32 listed rows to hand out
     int staged;                  // window is in shared memory (else: same slots, fetched from global memory)
     int x0, y0, z0;              // first owned cell
+    int ghost_slots;             // window slots in a neighbour rank's layers (their payload may come from its memory)
+};
+// fused ghost reads of a Z-slab peer loop: where the neighbours' payload lives and what to wait for
+struct BrickGhost {
+    const float4* arr[2];
+    const int* counter[2];
+    const int* layout[2];        // the neighbours' (own_begin, own_end, ...) of the current sort
+    int delta[2];                // ghost sorted index + delta = the neighbour's sorted index of the same particle (set with `ready`)
+    int want;                    // completed writers the neighbours must have counted
+    int ready[2];
+    int own_begin, own_end;
 };
 struct BrickSmem {
     unsigned long long mbar;
     BrickShared tab[2];
+    BrickGhost gh;
 };
 
 struct Brick {
@@ -148,6 +175,7 @@ struct Brick {
     int parity;                  // which table set is in hand
     int wmax;
     bool stage, sorted;
+    bool fused;                  // payload array 1 of ghost particles is read from the neighbour ranks' memory
     int b_pre, o_pre, nf_pre, t_pre;   // thread 0: prefetched brick id, ordinal, listed-row count (brick after next) and ticket (the one after)
 };
 
@@ -222,6 +250,7 @@ __device__ __forceinline__ void brick_prepare(const Consts& c, const Dev& d, Bri
         }
         __syncwarp();
         int carry = 0;   // prefix sums of the run lengths (window slots) and of the owned-run lengths
+        int ghost = 0;   // slots of runs in a neighbour rank's layer
 #pragma unroll
         for (int r0 = 0; r0 < BRK_RUNS; r0 += 32) {
             const int r = r0 + lane;
@@ -229,7 +258,11 @@ __device__ __forceinline__ void brick_prepare(const Consts& c, const Dev& d, Bri
             const int inc = brk_warp_inclusive_scan(len);
             if (r < BRK_RUNS) tab.S[r] = carry + inc - len;
             carry += __shfl_sync(0xffffffffu, inc, 31);
+            const int z = z0 - 1 + r / BRK_RY;
+            if (r < BRK_RUNS && ((c.ghost_lo && z == c.z_lo - 1) || (c.ghost_hi && z == c.z_hi))) ghost += len;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ghost += __shfl_xor_sync(0xffffffffu, ghost, o);
         int ocarry = 0;
 #pragma unroll
         for (int q0 = 0; q0 < BRK_OWN_RUNS; q0 += 32) {
@@ -248,6 +281,7 @@ __device__ __forceinline__ void brick_prepare(const Consts& c, const Dev& d, Bri
             tab.OP[BRK_OWN_RUNS] = ocarry;
             tab.staged = bk.stage && carry <= bk.wmax;
             tab.x0 = x0; tab.y0 = y0; tab.z0 = z0;
+            tab.ghost_slots = ghost;
             if (carry > d.brick_ctl[BCTL_WMAX_SEEN]) atomicMax(d.brick_ctl + BCTL_WMAX_SEEN, carry);
             if (bk.stage && carry > bk.wmax) atomicAdd(d.brick_ctl + BCTL_OVERFLOWS, 1);
         }
@@ -255,10 +289,24 @@ __device__ __forceinline__ void brick_prepare(const Consts& c, const Dev& d, Bri
     __syncwarp();
 }
 
+// Wait (one lane) until the neighbour on `side` has completed the sweep whose output this one reads, then fix the index
+// shift between my ghost rows and its owned rows: my lower ghosts are the lower neighbour's last owned rows, my upper
+// ones the upper neighbour's first (its layout words were published by its sort, long before that sweep).
+__device__ __forceinline__ void brick_ghost_wait(BrickGhost& gh, int side) {
+    if (*(volatile int*)&gh.ready[side] != 0) return;
+    while (brk_ld_volatile_i32(gh.counter[side]) < gh.want) __nanosleep(64);
+    __threadfence_system();
+    const int d = side == 0 ? brk_ld_volatile_i32(gh.layout[0] + 1) - gh.own_begin : brk_ld_volatile_i32(gh.layout[1] + 0) - gh.own_end;
+    *(volatile int*)&gh.delta[side] = d;   // several warps may get here at once: they all store the same value
+    __threadfence_block();
+    *(volatile int*)&gh.ready[side] = 1;
+}
+
 // CTA-wide, once per kernel: barrier, first tickets, tables of the first brick.
 // stage: copy windows into shared memory; sorted: walk the rows through the list build's row lists.
 __device__ __forceinline__ void brick_begin(const Consts& c, const Dev& d, Brick& bk, BrickSmem* smem, float4* window, int wmax,
-                                            const float4* g0, const float4* g1, const float4* g2, bool stage, bool sorted) {
+                                            const float4* g0, const float4* g1, const float4* g2, bool stage, bool sorted,
+                                            const PeerLinks* peer = nullptr) {
     bk.smem = smem;
     bk.a0 = smem_u32(window); bk.a1 = bk.a0 + 16u * (unsigned)wmax; bk.a2 = bk.a1 + 16u * (unsigned)wmax;
     bk.g0 = g0; bk.g1 = g1; bk.g2 = g2;
@@ -268,7 +316,21 @@ __device__ __forceinline__ void brick_begin(const Consts& c, const Dev& d, Brick
     bk.stage = stage; bk.sorted = sorted;
     bk.b_pre = -1; bk.o_pre = 0; bk.nf_pre = -1; bk.t_pre = 0;
     bk.sh = &smem->tab[0];
+    bk.fused = peer != nullptr && peer->fused != 0;
     if (threadIdx.x == 0) {
+        if (bk.fused) {   // where the neighbours keep my ghosts' payload, and how far they must have counted
+            BrickGhost& gh = smem->gh;
+            for (int side = 0; side < 2; side++) {
+                gh.arr[side] = peer->ghost_arr[side];
+                gh.counter[side] = peer->ghost_counter[side];
+                gh.layout[side] = peer->ghost_layout[side];
+                gh.ready[side] = 0;
+                gh.delta[side] = 0;
+            }
+            gh.want = *(volatile const int*)peer->my_counter;
+            gh.own_begin = peer->own_begin;
+            gh.own_end = peer->own_end;
+        }
         mbar_init(&smem->mbar, 1);
         fence_mbar_init();
         brick_prefetch(d, bk, atomicAdd(d.brick_ctl + BCTL_TICKET, 1));
@@ -285,25 +347,47 @@ __device__ __forceinline__ bool brick_stage(const Consts& c, const Dev& d, Brick
     BrickShared& sh = *bk.sh;
     if (sh.brick < 0) return false;
     const int tid = threadIdx.x;
+    const bool ghosts = bk.fused && NARR > 1 && sh.ghost_slots > 0;   // uniform over the CTA
     if (sh.staged) {
         // lane 0 of every warp issues the copies of runs warp, warp + BRK_WARPS, ...: the issue is spread over the four
         // schedulers instead of being serialised inside one warp (UBLKCP takes its operands from uniform registers)
-        for (int r = (tid & 31) ? BRK_RUNS : (tid >> 5); r < BRK_RUNS; r += BRK_WARPS) {
+        const int lane = tid & 31;
+        for (int r = tid >> 5; r < BRK_RUNS; r += BRK_WARPS) {
             const int g = sh.T[r][0], n = sh.T[r][BRK_TW - 1] - g, s = sh.S[r];
-            if (n > 0) {
+            if (n <= 0) continue;
+            int side = -1;   // run of a neighbour rank's layer whose payload is read from that rank's memory
+            if (ghosts) {
+                const int z = sh.z0 - 1 + r / BRK_RY;
+                side = (c.ghost_lo && z == c.z_lo - 1) ? 0 : ((c.ghost_hi && z == c.z_hi) ? 1 : -1);
+            }
+            if (lane == 0) {
                 tma_bulk_load(bk.a0 + 16u * s, bk.g0 + g, (unsigned)n * 16u, &bk.smem->mbar);
-                if (NARR > 1) tma_bulk_load(bk.a1 + 16u * s, bk.g1 + g, (unsigned)n * 16u, &bk.smem->mbar);
+                if (NARR > 1 && side < 0) tma_bulk_load(bk.a1 + 16u * s, bk.g1 + g, (unsigned)n * 16u, &bk.smem->mbar);
                 if (NARR > 2) tma_bulk_load(bk.a2 + 16u * s, bk.g2 + g, (unsigned)n * 16u, &bk.smem->mbar);
+            }
+            if (side >= 0) {
+                BrickGhost& gh = bk.smem->gh;
+                if (lane == 0) brick_ghost_wait(gh, side);
+                __syncwarp();
+                const float4* src = gh.arr[side] + g + *(volatile int*)&gh.delta[side];
+                for (int e = lane; e < n; e += 32) sts128(bk.a1 + 16u * (unsigned)(s + e), brk_ld_volatile_f4(src + e));
             }
         }
         // the phase cannot complete before this arrival, whatever the copies have already delivered
-        if (tid == 0) mbar_arrive_expect_tx(&bk.smem->mbar, (unsigned)sh.S[BRK_RUNS] * 16u * NARR);
+        if (tid == 0) mbar_arrive_expect_tx(&bk.smem->mbar, ((unsigned)sh.S[BRK_RUNS] * NARR - (ghosts ? (unsigned)sh.ghost_slots : 0u)) * 16u);
+    } else if (ghosts) {   // unstaged window: its rows fetch ghost payloads from the neighbours one by one — after their sweep
+        if (tid == 0) {
+            BrickGhost& gh = bk.smem->gh;
+            for (int side = 0; side < 2; side++)
+                if (gh.arr[side]) brick_ghost_wait(gh, side);
+        }
     }
     if (tid < 32) brick_prepare(c, d, bk, bk.smem->tab[bk.parity ^ 1]);   // overlaps the copies
     if (sh.staged) {
         mbar_wait(&bk.smem->mbar, bk.phase);
         bk.phase ^= 1u;
     }
+    if (ghosts) __syncthreads();   // ghost runs were stored by ordinary instructions of several warps / the wait above
     return true;
 }
 
@@ -354,6 +438,16 @@ __device__ __forceinline__ BrickRow brick_own_row(const Brick& bk, int t) {
 __device__ __forceinline__ float4 brick_own_load(const Brick& bk, BrickRow row, int which) {
     if (bk.sh->staged) return lds128((which == 0 ? bk.a0 : (which == 1 ? bk.a1 : bk.a2)) + 16u * (unsigned)row.slot);
     return (which == 0 ? bk.g0 : (which == 1 ? bk.g1 : bk.g2))[row.i];
+}
+
+// payload array 1 of sorted index j from global memory: a ghost's comes from its owner rank inside a fused peer loop
+__device__ __forceinline__ float4 brick_payload1(const Brick& bk, int j) {
+    if (bk.fused) {
+        const BrickGhost& gh = bk.smem->gh;
+        if (j < gh.own_begin && gh.arr[0]) return brk_ld_volatile_f4(gh.arr[0] + j + *(volatile const int*)&gh.delta[0]);
+        if (j >= gh.own_end && gh.arr[1]) return brk_ld_volatile_f4(gh.arr[1] + j + *(volatile const int*)&gh.delta[1]);
+    }
+    return __ldg(bk.g1 + j);
 }
 
 // Neighbour-list rows: nbr_kmax 16-bit words per particle, word 0 = number of neighbours n (SPH_ROW_NO_LIST: the row
@@ -438,7 +532,7 @@ __device__ __forceinline__ int brick_neighbors(const Consts& c, const Dev& d, co
                     const int slot = NC ? (int)__ldg(row + k) : (int)((const volatile unsigned short*)row)[k];
                     const int j = brick_slot_to_index(sh, slot);
                     const float4 pj = __ldg(bk.g0 + j);
-                    const float4 aj = NARR > 1 ? __ldg(bk.g1 + j) : pj;
+                    const float4 aj = NARR > 1 ? brick_payload1(bk, j) : pj;
                     const float4 bj = NARR > 2 ? __ldg(bk.g2 + j) : pj;
                     const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
                     visit(NbrRef{slot, true}, pj, aj, bj, R, dist2(R));
@@ -449,7 +543,7 @@ __device__ __forceinline__ int brick_neighbors(const Consts& c, const Dev& d, co
     }
     int n = 0;
     for_all_neighbors(c, d, i, pi, [&](int j, float4 pj, float3 R, float r2) {
-        const float4 aj = NARR > 1 ? __ldg(bk.g1 + j) : pj;
+        const float4 aj = NARR > 1 ? brick_payload1(bk, j) : pj;
         const float4 bj = NARR > 2 ? __ldg(bk.g2 + j) : pj;
         visit(NbrRef{j, false}, pj, aj, bj, R, r2);
         n++;

@@ -42,6 +42,7 @@ struct Consts {
     float pcisph_k;
     float corr_thresh;   // m_eps * dt of the DFSPH correction steps (DFSPH.py:175,258)
     int z_lo, z_hi;   // owned cell layers (whole grid unless the handle is a slab)
+    int ghost_lo, ghost_hi;   // 1: a neighbour rank owns the layer z_lo - 1 / z_hi (its particles are ghosts here)
     int row_begin, row_end;   // rows the kernels update: [0, N) or, for a Z-slab, the owned index range
     int nbx, nby, nbz;        // brick grid: ceil(grid_num / SPH_BRICK_{X,Y,Z})  (sph_brick.cuh)
 };

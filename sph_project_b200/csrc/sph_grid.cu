@@ -180,16 +180,28 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_flag_bricks(Consts c, Dev d) {
     }
 }
 
-// Ascending list of the flagged bricks + the control words of the persistent brick kernels (one block).
-__global__ void __launch_bounds__(1024) k_brick_compact(Dev d, int nbricks) {
+// List of the flagged bricks + the control words of the persistent brick kernels (one block).  Only the brick layers
+// that can hold rows of this rank are scanned; bricks whose window reaches into a neighbour rank's layer (ghosts) go
+// last, so that the sweeps of a peer loop meet them when the neighbour has long finished the sweep they depend on.
+__global__ void __launch_bounds__(1024) k_brick_compact(Consts c, Dev d, int nbricks) {
+    const int per_layer = c.nbx * c.nby;
+    const int bz_lo = max(c.z_lo / BRK_Z, 0), bz_hi = min((c.z_hi - 1) / BRK_Z + 1, c.nbz);
+    const int first = bz_lo * per_layer, last = min(bz_hi * per_layer, nbricks);
     int carry = 0;
-    for (int base = 0; base < nbricks; base += 1024) {
-        const int b = base + threadIdx.x;
-        const int f = b < nbricks ? (d.brick_flag[b] != 0) : 0;
-        int total;
-        const int ex = block_exclusive_scan(f, &total);
-        if (f) d.brick_list[carry + ex] = b;
-        carry += total;
+    for (int pass = 0; pass < 2; pass++) {
+        for (int base = first; base < last; base += 1024) {
+            const int b = base + threadIdx.x;
+            int f = 0;
+            if (b < last && d.brick_flag[b] != 0) {
+                const int z0 = (b / per_layer) * BRK_Z;   // window layers z0 - 1 .. z0 + BRK_Z
+                const bool edge = (c.ghost_lo && z0 - 1 <= c.z_lo - 1) || (c.ghost_hi && z0 + BRK_Z >= c.z_hi);
+                f = (edge ? 1 : 0) == pass;
+            }
+            int total;
+            const int ex = block_exclusive_scan(f, &total);
+            if (f) d.brick_list[carry + ex] = b;
+            carry += total;
+        }
     }
     if (threadIdx.x == 0) {
         d.brick_ctl[BCTL_ACTIVE] = carry;
@@ -222,7 +234,7 @@ void sph_bricks_refresh(SphHandle* h) {
     if (!h->sorted_valid) return;   // the next sort rebuilds it
     cudaMemsetAsync(h->d.brick_flag, 0, sizeof(int) * (size_t)h->nbricks, h->stream);
     if (h->c.N > 0) k_flag_bricks<<<(h->c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, h->stream>>>(h->c, h->d);
-    k_brick_compact<<<1, 1024, 0, h->stream>>>(h->d, h->nbricks);
+    k_brick_compact<<<1, 1024, 0, h->stream>>>(h->c, h->d, h->nbricks);
     h->launches += 2;
 }
 
@@ -276,7 +288,7 @@ int sph_sort_particles(SphHandle* h) {
     }
     {
         SphProf p(h, "k_brick_compact");
-        k_brick_compact<<<1, 1024, 0, st>>>(d, h->nbricks);
+        k_brick_compact<<<1, 1024, 0, st>>>(c, d, h->nbricks);
         h->launches++;
     }
     h->sorted_valid = true;

@@ -58,9 +58,16 @@ struct PeerLinks {
     PeerCtl* mine;
     PeerCtl* const* all;                 // device array [world] of every rank's block (own included)
     int world, rank;
+    // fused ghost reads: the sweep stages the ghost runs of its payload array straight from the neighbours' live arrays
+    int fused;                           // 0: ghosts were refreshed into the local array before the launch
+    const float4* ghost_arr[2];          // lower / upper neighbour's payload array (null: no neighbour)
+    const int* ghost_counter[2];         // their completion counters for that payload
+    const int* ghost_layout[2];          // their layout words (own_begin, own_end, ...)
+    const int* my_counter;               // this rank's counter: the neighbours must have counted as far
+    int own_begin, own_end;              // my owned index range: ghosts lie below / above it
 };
 bool sph_slab_peers_ready(const SphHandle* h);
-PeerLinks sph_slab_peer_links(const SphHandle* h);
+PeerLinks sph_slab_peer_links(const SphHandle* h, int fuse_field = 0 /* GHOST_VEL | GHOST_AUX: read that payload's ghosts from the neighbours */);
 void sph_slab_peer_pull(SphHandle* h, int which /* GHOST_VEL | GHOST_AUX */, bool speculative);
 void sph_slab_publish_layout(SphHandle* h);
 

@@ -379,14 +379,30 @@ __global__ void __launch_bounds__(256) k_peer_pull(float4* mine_arr, const float
 
 bool sph_slab_peers_ready(const SphHandle* h) { return h->slab && h->slab->peers_ready; }
 
-PeerLinks sph_slab_peer_links(const SphHandle* h) {
+PeerLinks sph_slab_peer_links(const SphHandle* h, int fuse_field) {
     PeerLinks l;
-    l.mine = nullptr; l.all = nullptr; l.world = 0; l.rank = 0;
-    if (sph_slab_peers_ready(h) && h->peer_loop) {
-        l.mine = h->slab->ctl;
-        l.all = h->slab->d_peer_ctl;
-        l.world = h->slab->world;
-        l.rank = h->slab->rank;
+    memset(&l, 0, sizeof l);
+    if (!(sph_slab_peers_ready(h) && h->peer_loop)) return l;
+    const SlabState* s = h->slab;
+    l.mine = s->ctl;
+    l.all = s->d_peer_ctl;
+    l.world = s->world;
+    l.rank = s->rank;
+    if (fuse_field) {
+        const bool aux = fuse_field == GHOST_AUX;
+        const int half = (h->d.vm == s->export_vm) ? 0 : 1;   // which half of the neighbours' velocity ping-pong is current
+        const int nb[2] = {s->rank - 1, s->rank + 1};
+        for (int side = 0; side < 2; side++) {
+            if (nb[side] < 0 || nb[side] >= s->world) continue;
+            const PeerCtl* pc = s->peer_ctl[nb[side]];
+            l.ghost_arr[side] = aux ? s->peer_aux[side] : s->peer_vm[side][half];
+            l.ghost_counter[side] = aux ? &pc->aux_count : &pc->vel_count;
+            l.ghost_layout[side] = pc->layout;
+        }
+        l.my_counter = aux ? &s->ctl->aux_count : &s->ctl->vel_count;
+        l.own_begin = s->own_begin;
+        l.own_end = s->own_end;
+        l.fused = 1;
     }
     return l;
 }
@@ -456,6 +472,9 @@ int sph_slab_init(SphHandle* h, int32_t rank, int32_t world, const void* unique_
     SlabState* s = new SlabState();
     h->slab = s;
     s->rank = rank; s->world = world; s->z_lo = z_lo; s->z_hi = z_hi;
+    h->c.z_lo = z_lo; h->c.z_hi = z_hi;
+    h->c.ghost_lo = rank > 0 ? 1 : 0;
+    h->c.ghost_hi = rank + 1 < world ? 1 : 0;
     cudaSetDevice(h->P.device);
     ncclUniqueId id;
     memcpy(&id, unique_id128, sizeof id);

@@ -81,10 +81,10 @@ __device__ __forceinline__ void brick_rows(const Consts& c, const Dev& d, const 
 // lists: the neighbour lists (and with them the sorted row order) are valid.
 template <int NARR, class RowFn>
 __device__ __forceinline__ void brick_for_rows(const Consts& c, const Dev& d, int wmax, bool lists, const float4* g0, const float4* g1,
-                                               const float4* g2, RowFn&& row) {
+                                               const float4* g2, RowFn&& row, const PeerLinks* peer = nullptr) {
     __shared__ BrickSmem bsm;
     Brick bk;
-    brick_begin(c, d, bk, &bsm, dyn_smem, wmax, g0, g1, g2, lists, lists);
+    brick_begin(c, d, bk, &bsm, dyn_smem, wmax, g0, g1, g2, lists, lists, peer);
     while (brick_stage<NARR>(c, d, bk)) {
         brick_rows(c, d, bk, row);
         brick_advance(bk);
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(SPH_BRICK_THREADS, SPH_BRICK_MINB2) kb_dfsph_d
             if (FUSED) { d.kappa_v[i] = kap; err += c.rho0 * adv; }
         }
         if (FUSED) d.aux[i] = make_float4(kap, kap / rho, rho, vi.w);
-    });
+    }, &ctl.peer);
     if (FUSED && ctl.mode != SOLVE_PLAIN) block_reduce_add(d.red + RED_ERR, (double)err);
     const bool last = brick_finish(d);
     if (FUSED && last) {
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(SPH_BRICK_THREADS, SPH_BRICK_MINB2) kb_dfsph_c
         });
         float4 v = d.vm[i];
         d.vm[i] = make_float4(v.x + dv.x, v.y + dv.y, v.z + dv.z, v.w);
-    });
+    }, &ctl.peer);
     if (brick_finish(d)) peer_signal(ctl.peer, false);   // velocities of my boundary layers are final
 }
 
@@ -789,25 +789,34 @@ void sph_launch_dfsph_alpha(SphHandle* h) {
     else LAUNCH_BRICK(1, (kb_pv_sweep<false, false>));
 }
 
-static SolveCtl solve_ctl(SphHandle* h, int mode, bool speculative, float eta) {
+static SolveCtl solve_ctl(SphHandle* h, int mode, bool speculative, float eta, int fuse_field = 0) {
     SolveCtl ctl;
     ctl.mode = mode;
     ctl.speculative = speculative ? 1 : 0;
     ctl.n_global = h->slab ? (float)h->n_global : (float)h->c.N;
     ctl.eta = eta;
-    ctl.peer = sph_slab_peer_links(h);
+    ctl.peer = sph_slab_peer_links(h, fuse_field);
     return ctl;
+}
+
+// Inside a peer loop, when the last writer of `field` signalled its completion: let the sweep read the ghosts of that
+// payload straight from the neighbours' memory (boundary bricks come last and wait for the signal there) instead of
+// refreshing the local ghost copies first.  The local copies stay marked stale.
+static bool fuse_ghost_reads(const SphHandle* h, int field) {
+    static const bool enabled = [] { const char* e = getenv("SPH_B200_PEER_FUSED"); return !(e && e[0] == '0'); }();
+    return enabled && h->peer_loop && h->lists_enabled && (h->ghost_stale & field) && (h->peer_signalled & field);
 }
 
 // fused: + kappa(_v) + aux; mode / speculative / eta: see SolveMode
 template <bool STAR>
 static void launch_density_change(SphHandle* h, bool fused, int mode, bool speculative, float eta) {
-    sph_ghost_sync(h, GHOST_PV | (STAR ? GHOST_RHO : 0) | GHOST_VEL);
+    const bool fuse = fuse_ghost_reads(h, GHOST_VEL);
+    sph_ghost_sync(h, GHOST_PV | (STAR ? GHOST_RHO : 0) | (fuse ? 0 : GHOST_VEL));
     if (fused) {
         sph_ghost_dirty(h, GHOST_AUX);
         if (h->peer_loop) h->peer_signalled |= GHOST_AUX; else h->peer_signalled &= ~GHOST_AUX;
     }
-    const SolveCtl ctl = solve_ctl(h, fused ? mode : SOLVE_PLAIN, speculative, eta);
+    const SolveCtl ctl = solve_ctl(h, fused ? mode : SOLVE_PLAIN, speculative, eta, fuse ? GHOST_VEL : 0);
     if (sph_lists_ready(h)) {
         if (fused) LAUNCH_BRICK(2, (kb_dfsph_density_change<STAR, true, true>), ctl);
         else LAUNCH_BRICK(2, (kb_dfsph_density_change<STAR, true, false>), ctl);
@@ -831,8 +840,9 @@ void sph_launch_dfsph_density_star(SphHandle* h, bool fused, int mode, bool spec
 static void launch_correct(SphHandle* h, int aux_mode, bool speculative) {
     sph_ghost_sync(h, GHOST_PV | GHOST_RHO);
     if (aux_mode >= 0) prep_aux(h, aux_mode);
-    sph_ghost_sync(h, GHOST_AUX);
-    const SolveCtl ctl = solve_ctl(h, SOLVE_PLAIN, speculative, 0.0f);
+    const bool fuse = fuse_ghost_reads(h, GHOST_AUX);
+    if (!fuse) sph_ghost_sync(h, GHOST_AUX);
+    const SolveCtl ctl = solve_ctl(h, SOLVE_PLAIN, speculative, 0.0f, fuse ? GHOST_AUX : 0);
     const bool wrench = h->c.has_dynamic_rigid != 0;
     if (sph_lists_ready(h)) { if (wrench) LAUNCH_BRICK(2, (kb_dfsph_correct<true, true>), ctl); else LAUNCH_BRICK(2, (kb_dfsph_correct<true, false>), ctl); }
     else { if (wrench) LAUNCH_BRICK(2, (kb_dfsph_correct<false, true>), ctl); else LAUNCH_BRICK(2, (kb_dfsph_correct<false, false>), ctl); }
