@@ -184,22 +184,30 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_flag_bricks(Consts c, Dev d) {
 // that can hold rows of this rank are scanned; bricks whose window reaches into a neighbour rank's layer (ghosts) go
 // last, so that the sweeps of a peer loop meet them when the neighbour has long finished the sweep they depend on.
 __global__ void __launch_bounds__(1024) k_brick_compact(Consts c, Dev d, int nbricks) {
+    constexpr int ITEMS = 8;   // consecutive bricks per thread and trip
     const int per_layer = c.nbx * c.nby;
     const int bz_lo = max(c.z_lo / BRK_Z, 0), bz_hi = min((c.z_hi - 1) / BRK_Z + 1, c.nbz);
     const int first = bz_lo * per_layer, last = min(bz_hi * per_layer, nbricks);
+    const int passes = (c.ghost_lo || c.ghost_hi) ? 2 : 1;
     int carry = 0;
-    for (int pass = 0; pass < 2; pass++) {
-        for (int base = first; base < last; base += 1024) {
-            const int b = base + threadIdx.x;
-            int f = 0;
-            if (b < last && d.brick_flag[b] != 0) {
-                const int z0 = (b / per_layer) * BRK_Z;   // window layers z0 - 1 .. z0 + BRK_Z
-                const bool edge = (c.ghost_lo && z0 - 1 <= c.z_lo - 1) || (c.ghost_hi && z0 + BRK_Z >= c.z_hi);
-                f = (edge ? 1 : 0) == pass;
+    for (int pass = 0; pass < passes; pass++) {
+        for (int base = first; base < last; base += 1024 * ITEMS) {
+            const int b0 = base + (int)threadIdx.x * ITEMS;
+            unsigned mask = 0;
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++) {
+                const int b = b0 + k;
+                if (b < last && d.brick_flag[b] != 0) {
+                    const int z0 = (b / per_layer) * BRK_Z;   // window layers z0 - 1 .. z0 + BRK_Z
+                    const bool edge = (c.ghost_lo && z0 - 1 <= c.z_lo - 1) || (c.ghost_hi && z0 + BRK_Z >= c.z_hi);
+                    if ((edge ? 1 : 0) == pass) mask |= 1u << k;
+                }
             }
             int total;
-            const int ex = block_exclusive_scan(f, &total);
-            if (f) d.brick_list[carry + ex] = b;
+            int pos = carry + block_exclusive_scan(__popc(mask), &total);
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++)
+                if (mask & (1u << k)) d.brick_list[pos++] = b0 + k;
             carry += total;
         }
     }
