@@ -453,6 +453,9 @@ class BaseContainer:
         keep = self.slab.owned(positions)
         uids = (self._next_uid + np.arange(new_particles_num, dtype=np.int32))[keep]
         self._next_uid += new_particles_num
+        # particle_num of the whole domain as of now (the DFSPH error averages over it, DFSPH.py:211,294): every rank
+        # sees every insertion, whoever keeps the particles
+        self._engine.slab_set_global_particle_num(self._next_uid)
         if not keep.any():
             return
         pick = lambda a, w: np.asarray(a).reshape(new_particles_num, *([w] if w > 1 else []))[keep]

@@ -542,6 +542,8 @@ int sph_add_particles(SphHandle* h, int32_t object_id, int32_t n, const float* x
     CUDA_TRY(h, cudaMemcpyAsync(d.material + o, material, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(h, cudaMemcpyAsync(d.is_dynamic + o, is_dynamic, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
     CUDA_TRY(h, cudaMemcpyAsync(d.color + 3 * o, color, 12 * (size_t)n, cudaMemcpyHostToDevice, st));
+    // Z-slabs: the slots behind the live particles still carry the marks of what the last sort retired there
+    CUDA_TRY(h, cudaMemsetAsync(d.ghost_slot + o, 0, 4 * (size_t)n, st));   // 0 = owned
     CUDA_TRY(h, cudaStreamSynchronize(st));   // host vectors go out of scope
     c.N += n;
     h->sorted_valid = false;

@@ -32,6 +32,14 @@ def _skew_exp(w, dt):
     return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
 
 
+def _euler_xyz(rpy):
+    """Rotation matrix of PyBullet's getQuaternionFromEuler([roll, pitch, yaw]): R = Rz(yaw) Ry(pitch) Rx(roll)."""
+    (cr, sr), (cp, sp), (cy, sy) = [(np.cos(a), np.sin(a)) for a in rpy]
+    return np.array([[cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr],
+                     [sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr],
+                     [-sp, cp * sr, cp * cr]], dtype=np.float64)
+
+
 class _Body:
     def __init__(self, obj_id, mass, inertia_body, x, R, v, w, local_vertices):
         self.obj_id = obj_id
@@ -91,7 +99,9 @@ class PyBulletSolver:
             translation = np.array(rigid_body["translation"], dtype=np.float64)
             angle = rigid_body["rotationAngle"] / 360 * (2 * np.pi)
             axis = np.array(rigid_body["rotationAxis"], dtype=np.float64)
-            R = _skew_exp(axis / max(np.linalg.norm(axis), 1e-30), angle) if np.linalg.norm(axis) > 0 else np.eye(3)
+            # upstream turns axis * angle into EULER angles (roll, pitch, yaw) — p.getQuaternionFromEuler(axis * angle),
+            # bullet_solver.py:102-106 — not into an axis-angle rotation; the two agree for coordinate axes only
+            R = _euler_xyz(axis * angle)
             velocity = np.array(rigid_body["velocity"], dtype=np.float64)
             # body-frame particles (the container inserted them unplaced, base_container.py:618-625)
             pts = np.asarray(rigid_body["voxelizedPoints"], dtype=np.float64)

@@ -92,11 +92,14 @@ class SlabContext:
         return int(c[lo:hi].sum() * slack) + extra
 
 
-def slab_parity_check(rank: int, world: int, local_rank: int, method: str = "dfsph", steps: int = 30) -> Optional[dict]:
+def slab_parity_check(rank: int, world: int, local_rank: int, method: str = "dfsph", steps: int = 30,
+                      late_block: bool = False) -> Optional[dict]:
     """Every rank steps its slab of a small dam break; rank 0 also steps the same scene unsharded on its GPU and
     compares positions / velocities by uid (north_star tolerance 1e-4 relative), solver iteration counts and particle
     conservation.  Needs an initialised torch.distributed process group (one rank per GPU).  Returns the report on rank
-    0 (key "ok"), None elsewhere."""
+    0 (key "ok"), None elsewhere.
+    late_block: a second fluid block enters after 5 steps inside the LAST rank's slab only, so one rank alone adds
+    particles mid-run and the step runs task by task through the Python solver (the hooks in the middle of `_step`)."""
     import contextlib
     import sys
 
@@ -114,6 +117,10 @@ def slab_parity_check(rank: int, world: int, local_rank: int, method: str = "dfs
             "viscosity": 10.0, "viscosity_b": 5.0, "timeStepSize": dt, "exportFrame": False, "exportPly": False, "exportObj": False},
         "FluidBlocks": [{"objectId": 0, "start": [0.1, 0.1, 0.1], "end": [0.3, 0.5, 0.4 * world + 0.3], "translation": [0, 0, 0],
                          "scale": [1, 1, 1], "velocity": [0.0, -1.0, 0.3], "density": 1000.0, "color": [50, 100, 200], "entryTime": -1.0}]}
+    if late_block:
+        scene["FluidBlocks"].append({"objectId": 1, "start": [0.38, 0.1, 0.4 * world + 0.1], "end": [0.5, 0.3, 0.4 * world + 0.3],
+                                     "translation": [0, 0, 0], "scale": [1, 1, 1], "velocity": [0.0, -0.5, 0.0], "density": 1000.0,
+                                     "color": [200, 100, 50], "entryTime": 5.5 * dt})
     C, S = (DFSPHContainer, DFSPHSolver) if method == "dfsph" else (WCSPHContainer, WCSPHSolver)
 
     def build(slab):
@@ -128,8 +135,12 @@ def slab_parity_check(rank: int, world: int, local_rank: int, method: str = "dfs
         it = [0, 0]
         for _ in range(steps):
             st = s.step()
-            it[0] += st.total_dfsph_iterations
-            it[1] += st.total_dfsph_iterations_v
+            if st is not None:          # native step
+                it[0] += st.total_dfsph_iterations
+                it[1] += st.total_dfsph_iterations_v
+            elif method == "dfsph":     # task-by-task step (objects pending): the Python loops keep the counts
+                it[0] += s.last_iterations[0]
+                it[1] += s.last_iterations_v[0]
         return it
 
     c, s = build((rank, world))
@@ -165,7 +176,7 @@ def slab_parity_check(rank: int, world: int, local_rank: int, method: str = "dfs
     its = gathered[0][3]
     same_it = abs(its[0] - itr[0]) <= 1 and abs(its[1] - itr[1]) <= 1
     ok = bool(conserved and ex < 1e-4 and ev < 1e-2 and same_it)
-    return {"method": method, "world": world, "steps": steps, "particles": int(nr), "conserved": conserved,
+    return {"method": method, "world": world, "steps": steps, "late_block": late_block, "particles": int(nr), "conserved": conserved,
             "max_rel_position_error": ex, "max_rel_velocity_error": ev, "iterations_slab": [int(a) for a in its],
             "iterations_single": [int(a) for a in itr], "owned_per_rank": [int(g[0].size) for g in gathered],
             "halo_calls_rank0": gathered[0][4], "ok": ok}

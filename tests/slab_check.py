@@ -23,7 +23,7 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    res = slab_parity_check(rank, world, local, method=method, steps=steps)
+    res = slab_parity_check(rank, world, local, method=method, steps=steps, late_block=os.environ.get("SLAB_CHECK_LATE_BLOCK") == "1")
     ok = True
     if rank == 0:
         print(json.dumps(dict(res, slab_check=method)), flush=True)

@@ -16,11 +16,13 @@ def _gpus():
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
 
 
-@pytest.mark.parametrize("method", ["dfsph", "wcsph"])
-def test_two_slabs_match_single_gpu(method):
+@pytest.mark.parametrize("method,late", [("dfsph", False), ("wcsph", False), ("dfsph", True), ("wcsph", True)])
+def test_two_slabs_match_single_gpu(method, late):
+    """late: a block enters after 5 steps inside rank 1's slab only — one rank alone adds particles, the other must
+    still issue the same collectives (rank-uniform flags), and the steps run task by task through the Python solver."""
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
-    env = dict(os.environ, SLAB_CHECK_METHOD=method, SLAB_CHECK_STEPS="30")
+    env = dict(os.environ, SLAB_CHECK_METHOD=method, SLAB_CHECK_STEPS="30", SLAB_CHECK_LATE_BLOCK="1" if late else "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29531", os.path.join(ROOT, "tests", "slab_check.py")]
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)

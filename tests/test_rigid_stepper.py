@@ -59,3 +59,17 @@ def test_two_way_coupling_with_dfsph(tmp_path):
             (np.abs(by_uid(c, c.particle_positions)[:, 2] - 0.3) < 0.05)
     assert v[under, 1].mean() < -9.81 * n * 1e-3 - 0.05    # fluid under the cube moves down faster than free fall
     assert (obj == 1).sum() == c.rigid_bodies[0]["particleNum"]
+
+
+def test_initial_orientation_is_euler_xyz_like_upstream():
+    """Upstream feeds rotationAxis * angle to p.getQuaternionFromEuler (bullet_solver.py:102-106): roll, pitch, yaw."""
+    from sph_project_b200.rigid_solver.bullet_solver import _euler_xyz, _skew_exp
+    for axis in np.eye(3):                       # coordinate axes: Euler and axis-angle agree
+        assert np.allclose(_euler_xyz(axis * 0.7), _skew_exp(axis, 0.7), atol=1e-12)
+    rpy = np.array([0.3, -0.5, 0.9])
+    R = _euler_xyz(rpy)
+    assert np.allclose(R @ R.T, np.eye(3), atol=1e-12) and np.isclose(np.linalg.det(R), 1.0)
+    Rx, Ry, Rz = (_skew_exp(a * t, 1.0) for a, t in zip(np.eye(3), rpy))
+    assert np.allclose(R, Rz @ Ry @ Rx, atol=1e-12)
+    oblique = np.array([1.0, 1.0, 0.0]) / np.sqrt(2.0) * 0.8
+    assert not np.allclose(_euler_xyz(oblique), _skew_exp(oblique / 0.8, 0.8), atol=1e-3)   # they differ off the axes
