@@ -449,7 +449,10 @@ class BaseContainer:
                                        new_particles_color)
             self._next_uid += new_particles_num
             return
-        # Z-slab: keep my layers only; uids stay the global insertion indices
+        # Z-slab: keep my layers only (as they are now: the library may have moved the boundaries towards the busier
+        # rank since the scene was cut); uids stay the global insertion indices
+        info = self._engine.slab_info()
+        self.slab.ranges[self.slab.rank] = (info.z_lo, info.z_hi)
         keep = self.slab.owned(positions)
         uids = (self._next_uid + np.arange(new_particles_num, dtype=np.int32))[keep]
         self._next_uid += new_particles_num

@@ -481,6 +481,40 @@ __device__ __forceinline__ int brick_neighbors(const Consts& c, const Dev& d, co
                 int base = 0;
 #pragma unroll 1
                 for (;;) {
+#ifdef SPH_BRICK_ROLLING
+                    if (ILP == 1) {
+                        // rolling prefetch: neighbour u + 1's window entries are requested before neighbour u is evaluated
+                        bool ok_n = base > 0 && base <= n;
+                        unsigned off_n = (w[0] << 4) & 0xffff0u;
+                        float4 pj_n = make_float4(0.f, 0.f, 0.f, 0.f), aj_n = pj_n, bj_n = pj_n;
+                        if (ok_n) {
+                            pj_n = lds128(a0 + off_n);
+                            if (NARR > 1) aj_n = A_HALF ? lds64(a1 + off_n) : lds128(a1 + off_n);
+                            if (NARR > 2) bj_n = lds128(a2 + off_n);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; u++) {
+                            const bool ok = ok_n;
+                            const unsigned off = off_n;
+                            const float4 pj = pj_n;
+                            const float4 aj = NARR > 1 ? aj_n : pj_n;
+                            const float4 bj = NARR > 2 ? bj_n : pj_n;
+                            if (u + 1 < 16) {
+                                ok_n = base + u + 1 <= n;
+                                off_n = ((u + 1) & 1) ? ((w[(u + 1) >> 1] >> 12) & 0xffff0u) : ((w[(u + 1) >> 1] << 4) & 0xffff0u);
+                                if (ok_n) {
+                                    pj_n = lds128(a0 + off_n);
+                                    if (NARR > 1) aj_n = A_HALF ? lds64(a1 + off_n) : lds128(a1 + off_n);
+                                    if (NARR > 2) bj_n = lds128(a2 + off_n);
+                                }
+                            }
+                            if (ok) {
+                                const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+                                visit(NbrRef{(int)(off >> 4), true}, pj, aj, bj, R, dist2(R));
+                            }
+                        }
+                    } else
+#endif
                     if (ILP == 1) {
 #pragma unroll
                         for (int u = 0; u < 16; u++) {

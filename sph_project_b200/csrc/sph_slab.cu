@@ -24,6 +24,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sph_kernels.h"
@@ -90,6 +91,9 @@ struct SlabState {
     int* d_counts = nullptr;              // [0..1] send counts lo/hi, [2..3] recv counts lo/hi
     int* h_ints = nullptr;                // pinned
     int64_t halo_bytes = 0, halo_calls = 0;
+    // re-balancing: every `rebalance_period` sorts a boundary may move by one cell layer towards the busier rank
+    int sorts = 0, rebalance_period = 0, rebalances = 0;
+    int* d_work = nullptr;                // [0..7] my work figures, [8..15] lower neighbour's, [16..23] upper neighbour's
     // peer memory (CUDA IPC over NVLink), optional
     PeerCtl* ctl = nullptr;                          // my control block (device)
     PeerCtl* peer_ctl[SPH_PEER_MAX_RANKS] = {nullptr};   // every rank's block as mapped here (own included)
@@ -188,6 +192,33 @@ __global__ void __launch_bounds__(SPH_BLOCK) k_slab_unpack(Dev d, const float* i
     d.ghost_slot[i] = slot;
 }
 
+// Work figures of a slab for the re-balancing: a fluid row costs ~20 boundary rows (the sweeps only work on fluid).
+// out[0] work of all owned particles, [1] / [2] work of the bottom / top owned layer, [3] / [4] their particle counts
+constexpr int SLAB_FLUID_WEIGHT = 20;
+__global__ void __launch_bounds__(SPH_BLOCK) k_slab_work(Consts c, Dev d, int z_lo, int z_hi, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int w = 0, lo = 0, hi = 0;
+    if (i < c.N && d.ghost_slot[i] == SLOT_OWNED) {
+        const float4 p = d.pv[i];
+        const int cz = cell_of(c, p.x, p.y, p.z).z;
+        if (cz >= z_lo && cz < z_hi) {
+            w = p.w > 0.0f ? SLAB_FLUID_WEIGHT : 1;
+            lo = cz == z_lo;
+            hi = cz == z_hi - 1;
+        }
+    }
+    const unsigned full = 0xffffffffu;
+    const int w_all = __reduce_add_sync(full, w), w_lo = __reduce_add_sync(full, lo ? w : 0), w_hi = __reduce_add_sync(full, hi ? w : 0);
+    const int n_lo = __reduce_add_sync(full, lo), n_hi = __reduce_add_sync(full, hi);
+    if ((threadIdx.x & 31) == 0) {
+        if (w_all) atomicAdd(out + 0, w_all);
+        if (w_lo) atomicAdd(out + 1, w_lo);
+        if (w_hi) atomicAdd(out + 2, w_hi);
+        if (n_lo) atomicAdd(out + 3, n_lo);
+        if (n_hi) atomicAdd(out + 4, n_hi);
+    }
+}
+
 int neighbour(const SlabState* s, int side) {
     const int r = side == 0 ? s->rank - 1 : s->rank + 1;
     return (r < 0 || r >= s->world) ? -1 : r;
@@ -253,8 +284,67 @@ int exchange_phase(SphHandle* h, int mode, int slot) {
 bool sph_is_slab(const SphHandle* h) { return h->slab != nullptr && h->slab->comm != nullptr; }
 
 // Migration + ghost re-import, run by the sort path right before the cell histogram.
+// Move slab boundaries by at most one cell layer each towards the busier rank.  Both ranks of a boundary decide from the
+// same six numbers (their work, the work and size of the layer that would change hands, their free capacity, their
+// thickness), so they always agree; the migration of the sort that follows carries the layer over.
+static int slab_rebalance(SphHandle* h) {
+    SlabState* s = h->slab;
+    Consts& c = h->c;
+    cudaStream_t st = h->stream;
+    int* mine = s->d_work;
+    CU_TRY(h, cudaMemsetAsync(mine, 0, 24 * sizeof(int), st));
+    if (c.N > 0) {
+        k_slab_work<<<(c.N + SPH_BLOCK - 1) / SPH_BLOCK, SPH_BLOCK, 0, st>>>(c, h->d, s->z_lo, s->z_hi, mine);
+        h->launches++;
+    }
+    int* hv = s->h_ints + 28;   // [5] free capacity, [6] thickness: host-known, appended to the device figures
+    hv[0] = c.cap - c.N;
+    hv[1] = s->z_hi - s->z_lo;
+    CU_TRY(h, cudaMemcpyAsync(mine + 5, hv, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+    NCCL_TRY(h, g_nccl.GroupStart());
+    for (int side = 0; side < 2; side++) {
+        const int nbr = neighbour(s, side);
+        if (nbr < 0) continue;
+        NCCL_TRY(h, g_nccl.Send(mine, 8, ncclInt32, nbr, s->comm, st));
+        NCCL_TRY(h, g_nccl.Recv(mine + 8 * (side + 1), 8, ncclInt32, nbr, s->comm, st));
+    }
+    NCCL_TRY(h, g_nccl.GroupEnd());
+    int v[24];
+    CU_TRY(h, cudaMemcpyAsync(v, mine, sizeof v, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    // boundary between a lower rank A and an upper rank B: returns -1 (A gives its top layer to B), +1 (B gives its
+    // bottom layer to A) or 0
+    auto decide = [](const int* A, const int* B) {
+        const long long diff = (long long)A[0] - B[0];
+        if (diff > 0 && diff > A[2] && A[6] > 3 && B[5] > A[4] + 4096) return -1;
+        if (diff < 0 && -diff > B[1] && B[6] > 3 && A[5] > B[3] + 4096) return +1;
+        return 0;
+    };
+    int moved = 0;
+    if (neighbour(s, 0) >= 0) {   // my lower boundary: the lower neighbour is A, I am B
+        const int m = decide(v + 8, v);
+        s->z_lo += m;
+        moved += m != 0;
+    }
+    if (neighbour(s, 1) >= 0) {   // my upper boundary: I am A
+        const int m = decide(v, v + 16);
+        s->z_hi += m;
+        moved += m != 0;
+    }
+    if (moved) {
+        c.z_lo = s->z_lo;
+        c.z_hi = s->z_hi;
+        s->rebalances += moved;
+    }
+    return SPH_OK;
+}
+
 int sph_slab_pre_sort(SphHandle* h) {
     SlabState* s = h->slab;
+    if (s->rebalance_period > 0 && s->world > 1 && h->rows_from_sort && (++s->sorts % s->rebalance_period) == 0) {
+        const int rc0 = slab_rebalance(h);
+        if (rc0) return rc0;
+    }
     // rank-uniform flags (read back with the first count exchange): [4] dynamic rigid particles anywhere,
     // [5] boundary volumes stale anywhere
     s->h_ints[16] = 0;
@@ -494,6 +584,11 @@ int sph_slab_init(SphHandle* h, int32_t rank, int32_t world, const void* unique_
         DALLOC(s->recvbuf[k], (size_t)s->buf_records * REC_WORDS * 4);
     }
     DALLOC(s->d_counts, 8 * sizeof(int));
+    DALLOC(s->d_work, 24 * sizeof(int));
+    {
+        const char* e = getenv("SPH_B200_REBALANCE");   // sorts between two re-balancing rounds, 0 = never
+        s->rebalance_period = e ? atoi(e) : 64;
+    }
 #undef DALLOC
     CU_TRY(h, cudaMallocHost((void**)&s->h_ints, 32 * sizeof(int)));
     h->n_global = global_particle_num;

@@ -147,8 +147,9 @@ def slab_parity_check(rank: int, world: int, local_rank: int, method: str = "dfs
     it = run(s)
     n = c.particle_num[None]
     own = c.owned_mask()
+    info = c.engine.slab_info()
     payload = (c.particle_uids.to_numpy(n)[own], c.particle_positions.to_numpy(n)[own], c.particle_velocities.to_numpy(n)[own],
-               it, int(c.engine.slab_info().halo_calls))
+               it, int(info.halo_calls), (int(info.z_lo), int(info.z_hi)), tuple(int(v) for v in c.slab.ranges[rank]))
     gathered = [None] * world
     dist.gather_object(payload, gathered if rank == 0 else None, dst=0)
     del c, s
@@ -179,4 +180,5 @@ def slab_parity_check(rank: int, world: int, local_rank: int, method: str = "dfs
     return {"method": method, "world": world, "steps": steps, "late_block": late_block, "particles": int(nr), "conserved": conserved,
             "max_rel_position_error": ex, "max_rel_velocity_error": ev, "iterations_slab": [int(a) for a in its],
             "iterations_single": [int(a) for a in itr], "owned_per_rank": [int(g[0].size) for g in gathered],
-            "halo_calls_rank0": gathered[0][4], "ok": ok}
+            "halo_calls_rank0": gathered[0][4], "layers_per_rank": [list(g[5]) for g in gathered],
+            "initial_layers_per_rank": [list(g[6]) for g in gathered], "ok": ok}
