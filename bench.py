@@ -663,10 +663,22 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.config == "c5_dam10m":
+        # the dam breaks ALONG z into slabs that start empty: room for the flood (slab.py, SlabContext.capacity)
+        os.environ.setdefault("SPH_B200_SLAB_SLACK", "4.0")
     if args.impl == "reference":
         run_reference(args, rank, world)
-    else:
+        return
+    try:
         run_gpu(args, rank, world, local_rank)
+    except BaseException:
+        # A rank that fails (e.g. SPH_E_CAPACITY) must die at once: the interpreter's teardown would wait for this
+        # rank's stream, which is parked in a collective its peers will never enter, and torchrun would never see
+        # the failure.  (Measured the hard way: profiles/r02_bench_8gpu_c5_pressurised_FAILED.txt.)
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
 
 
 if __name__ == "__main__":

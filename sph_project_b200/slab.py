@@ -84,12 +84,17 @@ class SlabContext:
         cz = cell_layer(positions[:, 2], self.dh, self.nz)
         return (cz >= self.z_lo) & (cz < self.z_hi)
 
-    def capacity(self, layer_counts: Sequence[int], slack: float = 1.3, extra: int = 65536) -> int:
+    def capacity(self, layer_counts: Sequence[int], slack: Optional[float] = None, extra: int = 65536) -> int:
         """Local particle capacity: owned layers + one ghost layer each side, with head-room for
-        migration imbalance."""
+        migration imbalance (SPH_B200_SLAB_SLACK, default 1.3; never more than the whole scene).  Scenes whose fluid
+        floods slabs that start empty (a dam break ALONG z) need a larger factor: a rank that runs out of room fails
+        with SPH_E_CAPACITY."""
+        import os
+        if slack is None:
+            slack = float(os.environ.get("SPH_B200_SLAB_SLACK", "1.3"))
         c = np.asarray(layer_counts, dtype=np.int64)
         lo, hi = max(self.z_lo - 1, 0), min(self.z_hi + 1, self.nz)
-        return int(c[lo:hi].sum() * slack) + extra
+        return min(int(c[lo:hi].sum() * slack), int(c.sum())) + extra
 
 
 def slab_parity_check(rank: int, world: int, local_rank: int, method: str = "dfsph", steps: int = 30,
