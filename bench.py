@@ -619,7 +619,9 @@ def run_gpu(args, rank, world, local_rank):
             line["slab_parity"] = slab_parity
             line["stats"]["slab"] = {"layers_rank0": [info.z_lo, info.z_hi], "owned_rank0": info.n_owned, "ghosts_rank0": info.n_ghost,
                                      "halo_refreshes_rank0": int(info.halo_calls), "bytes_sent_rank0": int(info.halo_bytes),
-                                     "transport": "NCCL send/recv + allreduce over NVLink, issued by the library on its stream"}
+                                     "transport": ("NCCL send/recv + all-reduce, issued by the library on its stream" if os.environ.get("SPH_B200_NO_PEER") == "1" else
+                                                   "per step: NCCL send/recv on the library's stream; inside the DFSPH loops: ghost payloads read from the "
+                                                   "neighbours' memory (CUDA IPC over NVLink) inside the sweeps, error sums stored into every rank's control block")}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

@@ -114,3 +114,34 @@ def test_state_transfer_reproduces_the_run():
     xb = bench.fields_by_uid(cb)[0]
     assert ia.total_dfsph_iterations == ib.total_dfsph_iterations
     assert np.abs(xa - xb).max() / np.abs(xa).max() < 1e-6
+
+
+def test_state_transfer_carries_parked_emitter_particles():
+    """With gravitationUpper set, fluid particles above it are parked as rigid until they cross it
+    (base_solver.py:651-677): the material is part of the state.  A transfer without it left those rows stuck in the
+    receiving simulation (found on config C4: 2.6e-3 relative position error after 21 steps)."""
+    import numpy as np
+    from helpers import oracle_library, scene
+    sc = scene("wcsph", domain_end=(0.6, 1.0, 0.6), block_start=(0.2, 0.3, 0.2), block_end=(0.4, 0.7, 0.4), dt=4e-4,
+               velocity=(0.0, -2.0, 0.0), g_upper=0.5, add_domain_box=False)
+    lib = oracle_library()
+    ca, sa = bench.make_sim(sc, lib)
+    sa.step(40)                                    # some parked rows have crossed the line and turned fluid by now
+    xs, vs, mats = bench.fields_by_uid(ca, with_material=True)
+    assert (mats == 1).any() and (mats == 2).any()
+    cb, sb = bench.make_sim(sc, lib)
+    assert not np.array_equal(bench.fields_by_uid(cb, with_material=True)[2], mats)   # a fresh run parks more rows
+    bench.load_state(cb, sb, xs, vs, mats)
+    sa.step(10), sb.step(10)
+    xa, xb = bench.fields_by_uid(ca)[0], bench.fields_by_uid(cb)[0]
+    assert np.abs(xa - xb).max() / np.abs(xa).max() < 1e-6
+
+
+def test_slab_capacity_knob(monkeypatch):
+    from sph_project_b200.slab import SlabContext
+    counts = [100] * 10
+    ctx = SlabContext(rank=1, world=2, dh=0.04, nz=10, ranges=[(0, 5), (5, 10)])
+    monkeypatch.delenv("SPH_B200_SLAB_SLACK", raising=False)
+    assert ctx.capacity(counts, extra=0) == int(600 * 1.3)            # owned layers + one ghost layer, x 1.3
+    monkeypatch.setenv("SPH_B200_SLAB_SLACK", "4.0")
+    assert ctx.capacity(counts, extra=0) == 1000                       # never more than the whole scene

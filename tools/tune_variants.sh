@@ -6,7 +6,7 @@
 # bench line counts.  Results: gpurun_out/variant_<name>.json (+ .err, .parity.log), table on stdout.
 mkdir -p gpurun_out
 LIBDIR=sph_project_b200/csrc
-for name in default minb10 minb12 unroll8 minb10_unroll8 block64 block256 idx_noalloc rec_evict_last idx_noalloc_rec_evict_last rec_l2_evict_last all_hints devconv; do
+for name in default b442 b442_256 b442_320 b342_256; do   # the VARIANTS of sph_project_b200/csrc/Makefile (window budgets: see tools/r02_call20.sh)
     if [ "$name" = default ]; then unset SPH_B200_LIBRARY; else export SPH_B200_LIBRARY="$PWD/$LIBDIR/variants/libsph_b200_$name.so"; fi
     [ "$name" = default ] || [ -f "$SPH_B200_LIBRARY" ] || { echo "$name: not built"; continue; }
     timeout 300 python -m pytest -q -m gpu -x "tests/test_gpu_fullsize.py::test_list_kernels_equal_window_walk_bitwise" \
