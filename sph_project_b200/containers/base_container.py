@@ -24,11 +24,61 @@ from ..utils import SimConfig
 _METHOD_IDS = {"wcsph": nat.METHOD_WCSPH, "pcisph": nat.METHOD_PCISPH, "dfsph": nat.METHOD_DFSPH}
 
 
+def _lattice_axes(lower_corner, extent, space, dim):
+    return [np.arange(lower_corner[i], lower_corner[i] + extent[i], space) for i in range(dim)]
+
+
 def _lattice(lower_corner, extent, space, dim):
     """Regular lattice like base_container.py:770-781: f64 arange per axis, ij-meshgrid, f32."""
-    axes = [np.arange(lower_corner[i], lower_corner[i] + extent[i], space) for i in range(dim)]
+    axes = _lattice_axes(lower_corner, extent, space, dim)
     grid = np.array(np.meshgrid(*axes, sparse=False, indexing="ij"), dtype=np.float32)
     return grid.reshape(dim, -1).transpose()
+
+
+# ---- the same lattices cut along z (Z-slabs, not upstream): a rank builds the rows of its own cell layers only.
+# The ij-meshgrid flattens x slowest / z fastest, so the row number of lattice point (ix, iy, iz) is known without
+# building the lattice, and the box-shell test of base_container.py:830-835 separates into one mask per axis.
+# tests/test_slab_host.py checks every function below against the full lattice filtered afterwards, bit for bit.
+
+def _lattice_rows(axes, kz):
+    """Rows of the 3-D lattice whose z index is in `kz` (ascending), in lattice order, and their row numbers in the
+    full lattice."""
+    nx, ny, nz = (len(a) for a in axes)
+    grid = np.array(np.meshgrid(axes[0], axes[1], axes[2][kz], sparse=False, indexing="ij"), dtype=np.float32)
+    rows = (np.arange(nx * ny, dtype=np.int64)[:, None] * nz + kz[None, :]).reshape(-1)
+    return grid.reshape(3, -1).transpose(), rows
+
+
+def _shell_masks(axes, lower_corner, cube_size, thickness):
+    """Per axis: which lattice coordinates lie inside a wall of the hollow box (the test is applied to the f32
+    coordinate, as `_box_shell` applies it to the f32 positions)."""
+    masks = []
+    for i, a in enumerate(axes):
+        a32 = a.astype(np.float32)
+        masks.append((a32 <= lower_corner[i] + thickness) | (a32 >= lower_corner[i] + cube_size[i] - thickness))
+    return masks
+
+
+def _shell_z_counts(masks):
+    """Shell particles per z index: a whole x-y plane inside the floor / lid, the rim of the plane elsewhere."""
+    mx, my, mz = masks
+    rim = int((mx[:, None] | my[None, :]).sum())
+    return np.where(mz, mx.size * my.size, rim).astype(np.int64)
+
+
+def _shell_rows(axes, masks, kz):
+    """Rows of the hollow box on the z indices `kz` (ascending), in lattice order, and their row numbers among the
+    shell rows of the whole box."""
+    nx, ny, nz = (len(a) for a in axes)
+    mx, my, mz = masks
+    wall = mx[:, None] | my[None, :]                       # columns inside an x or y wall keep every z
+    per_column = np.where(wall, nz, int(mz.sum())).astype(np.int64).reshape(-1)
+    column_base = (np.cumsum(per_column) - per_column).reshape(nx, ny)
+    rank_z = np.cumsum(mz) - 1                             # place of z index k among the kept z of an open column
+    keep = wall[:, :, None] | mz[kz][None, None, :]
+    rows = column_base[:, :, None] + np.where(wall[:, :, None], kz[None, None, :], rank_z[kz][None, None, :])
+    grid = np.array(np.meshgrid(axes[0], axes[1], axes[2][kz], sparse=False, indexing="ij"), dtype=np.float32)
+    return grid[:, keep].transpose(), rows[keep]
 
 
 class _NoOpScan:
@@ -250,21 +300,34 @@ class BaseContainer:
     def engine(self) -> nat.Engine:
         return self._engine
 
-    def _scene_positions(self):
-        """Every particle the scene will ever insert as (positions, is_fluid): box, blocks, mesh bodies; for the slab split."""
+    def _block_lattice(self, fluid):
+        offset = np.array(fluid["translation"])
+        start = np.array(fluid["start"]) + offset
+        end = np.array(fluid["end"]) + offset
+        return start, (end - start) * np.array(fluid["scale"])
+
+    def _scene_layers(self, nz):
+        """Particles per cell layer of everything the scene will ever insert, as (counts, is_fluid) per object, for the
+        slab split.  Box and blocks are counted from their lattice axes (no rank builds the whole scene); mesh bodies
+        from their voxelised points."""
+        from ..slab import cell_layer
         parts = []
+
+        def by_layer(z_values, per_value):
+            return np.bincount(cell_layer(z_values, self.dh, nz), weights=per_value, minlength=nz).astype(np.int64)
+
         if self.add_domain_box:
-            parts.append((self._box_shell(self.domain_box_start, self.domain_box_size, self.domain_box_thickness,
-                                          self.particle_spacing), False))
+            axes = _lattice_axes(self.domain_box_start, self.domain_box_size, self.particle_spacing, self.dim)
+            masks = _shell_masks(axes, self.domain_box_start, self.domain_box_size, self.domain_box_thickness)
+            parts.append((by_layer(axes[2], _shell_z_counts(masks)), False))
         for fluid in self.fluid_blocks:
-            offset = np.array(fluid["translation"])
-            start = np.array(fluid["start"]) + offset
-            end = np.array(fluid["end"]) + offset
-            parts.append((_lattice(start, (end - start) * np.array(fluid["scale"]), self.particle_spacing, self.dim), True))
-        for body in self.fluid_bodies:
-            parts.append((np.asarray(body["voxelizedPoints"], dtype=np.float32), True))
-        for body in self.rigid_bodies:
-            parts.append((np.asarray(body["voxelizedPoints"], dtype=np.float32), False))
+            axes = _lattice_axes(*self._block_lattice(fluid), self.particle_spacing, self.dim)
+            parts.append((by_layer(axes[2], np.full(len(axes[2]), len(axes[0]) * len(axes[1]))), True))
+        for bodies, is_fluid in ((self.fluid_bodies, True), (self.rigid_bodies, False)):
+            for body in bodies:
+                pts = np.asarray(body["voxelizedPoints"], dtype=np.float32)
+                if len(pts):
+                    parts.append((by_layer(pts[:, 2], np.ones(len(pts))), is_fluid))
         return parts
 
     # what a boundary particle costs relative to a fluid particle: it is sorted and gathered like any other, but the
@@ -274,15 +337,15 @@ class BaseContainer:
     SLAB_BOUNDARY_WEIGHT = 0.05
 
     def _make_slab_context(self, rank, world):
-        from ..slab import SlabContext, balanced_ranges, cell_layer
+        from ..slab import SlabContext, balanced_ranges
+        if self.dim != 3:
+            raise ValueError("Z-slabs need a 3-D scene")
         nz = int(self.grid_num[2])
         counts = np.zeros(nz, dtype=np.int64)
         work = np.zeros(nz, dtype=np.float64)
-        for pos, is_fluid in self._scene_positions():
-            if len(pos):
-                layer = np.bincount(cell_layer(pos[:, 2], self.dh, nz), minlength=nz)
-                counts += layer
-                work += layer * (1.0 if is_fluid else self.SLAB_BOUNDARY_WEIGHT)
+        for layer, is_fluid in self._scene_layers(nz):
+            counts += layer
+            work += layer * (1.0 if is_fluid else self.SLAB_BOUNDARY_WEIGHT)
         self._layer_counts = counts   # capacities follow the true counts, the cut follows the work
         return SlabContext(rank=int(rank), world=int(world), dh=float(self.dh), nz=nz,
                            ranges=balanced_ranges(np.rint(work * 100).astype(np.int64), int(world)))
@@ -449,48 +512,73 @@ class BaseContainer:
                                        new_particles_color)
             self._next_uid += new_particles_num
             return
-        # Z-slab: keep my layers only (as they are now: the library may have moved the boundaries towards the busier
-        # rank since the scene was cut); uids stay the global insertion indices
+        keep = self._slab_range_now().owned(positions)
+        pick = lambda a, w: np.asarray(a).reshape(new_particles_num, *([w] if w > 1 else []))[keep]
+        self._add_slab_rows(object_id, new_particles_num, np.flatnonzero(keep), positions[keep],
+                            pick(new_particles_velocity, self.dim), pick(new_particle_density, 1),
+                            pick(new_particle_pressure, 1), pick(new_particles_material, 1),
+                            pick(new_particles_is_dynamic, 1), pick(new_particles_color, 3))
+
+    def _slab_range_now(self):
+        """My layers as they are now: the library may have moved the boundaries towards the busier rank since the
+        scene was cut."""
         info = self._engine.slab_info()
         self.slab.ranges[self.slab.rank] = (info.z_lo, info.z_hi)
-        keep = self.slab.owned(positions)
-        uids = (self._next_uid + np.arange(new_particles_num, dtype=np.int32))[keep]
-        self._next_uid += new_particles_num
+        return self.slab
+
+    def _slab_z_indices(self, z_axis):
+        """Indices of the lattice z coordinates that fall into my layers."""
+        return np.flatnonzero(self._slab_range_now().owned_z(z_axis.astype(np.float32)))
+
+    def _add_slab_rows(self, object_id, total_num, rows, positions, velocity, density, pressure, material, is_dynamic,
+                       color):
+        """Z-slab insertion of an object with `total_num` particles of which this rank keeps `rows` (row numbers within
+        the object); uids stay the global insertion indices."""
+        uids = (self._next_uid + np.asarray(rows, dtype=np.int64)).astype(np.int32)
+        self._next_uid += total_num
         # particle_num of the whole domain as of now (the DFSPH error averages over it, DFSPH.py:211,294): every rank
         # sees every insertion, whoever keeps the particles
         self._engine.slab_set_global_particle_num(self._next_uid)
-        if not keep.any():
+        if not len(uids):
             return
-        pick = lambda a, w: np.asarray(a).reshape(new_particles_num, *([w] if w > 1 else []))[keep]
         n_before = self.particle_num[None]
-        self._engine.add_particles(object_id, positions[keep], pick(new_particles_velocity, self.dim),
-                                   pick(new_particle_density, 1), pick(new_particle_pressure, 1),
-                                   pick(new_particles_material, 1), pick(new_particles_is_dynamic, 1),
-                                   pick(new_particles_color, 3))
+        self._engine.add_particles(object_id, positions, velocity, density, pressure, material, is_dynamic, color)
         all_uids = np.concatenate([self._engine.get_field(F.UID, n_before), uids])
         self._engine.set_field(F.UID, all_uids)
 
-    def _add_lattice(self, object_id, positions, material, is_dynamic, color, density, pressure, velocity):
+    def _add_lattice(self, object_id, positions, material, is_dynamic, color, density, pressure, velocity, slab_rows=None):
+        """Insert lattice points with uniform attributes.  slab_rows = (total count of the object, row numbers of
+        `positions` within it): a Z-slab rank passes the rows of its own layers only."""
         n = positions.shape[0]
         if velocity is None:
             velocity_arr = np.zeros_like(positions, dtype=np.float32)
         else:
             velocity_arr = np.tile(np.asarray(velocity, dtype=np.float32), (n, 1))
-        self.add_particles(
-            object_id, n, positions, velocity_arr,
-            np.full(n, density if density is not None else 1000.0, dtype=np.float32),
-            np.full(n, pressure if pressure is not None else 0.0, dtype=np.float32),
-            np.full(n, material, dtype=np.int32), np.full(n, int(is_dynamic), dtype=np.int32),
-            np.tile(np.asarray(color, dtype=np.int32), (n, 1)))
-        return n
+        fields = (velocity_arr,
+                  np.full(n, density if density is not None else 1000.0, dtype=np.float32),
+                  np.full(n, pressure if pressure is not None else 0.0, dtype=np.float32),
+                  np.full(n, material, dtype=np.int32), np.full(n, int(is_dynamic), dtype=np.int32),
+                  np.tile(np.asarray(color, dtype=np.int32), (n, 1)))
+        if slab_rows is None:
+            self.add_particles(object_id, n, positions, *fields)
+            return n
+        total, rows = slab_rows
+        self._add_slab_rows(object_id, total, rows, positions, *fields)
+        return total
 
     def add_cube(self, object_id, lower_corner, cube_size, material, is_dynamic, color=(0, 0, 0), density=None,
                  pressure=None, velocity=None, space=None):
         """Particles spaced by `space` filling a box (base_container.py:753-798)."""
         if space is None:
             space = self.particle_diameter
-        positions = _lattice(lower_corner, cube_size, space, self.dim)
-        n = self._add_lattice(object_id, positions, material, is_dynamic, color, density, pressure, velocity)
+        if self.slab is None:
+            positions = _lattice(lower_corner, cube_size, space, self.dim)
+            n = self._add_lattice(object_id, positions, material, is_dynamic, color, density, pressure, velocity)
+        else:
+            axes = _lattice_axes(lower_corner, cube_size, space, self.dim)
+            positions, rows = _lattice_rows(axes, self._slab_z_indices(axes[2]))
+            n = self._add_lattice(object_id, positions, material, is_dynamic, color, density, pressure, velocity,
+                                  slab_rows=(len(axes[0]) * len(axes[1]) * len(axes[2]), rows))
         if material == self.material_fluid:
             self.fluid_particle_num[None] += n
 
@@ -507,8 +595,15 @@ class BaseContainer:
         """Hollow box of boundary particles (base_container.py:800-849)."""
         if space is None:
             space = self.particle_diameter
-        positions = self._box_shell(lower_corner, cube_size, thickness, space)
-        self._add_lattice(object_id, positions, material, is_dynamic, color, density, pressure, velocity)
+        if self.slab is None:
+            positions = self._box_shell(lower_corner, cube_size, thickness, space)
+            self._add_lattice(object_id, positions, material, is_dynamic, color, density, pressure, velocity)
+            return
+        axes = _lattice_axes(lower_corner, cube_size, space, self.dim)
+        masks = _shell_masks(axes, lower_corner, cube_size, thickness)
+        positions, rows = _shell_rows(axes, masks, self._slab_z_indices(axes[2]))
+        self._add_lattice(object_id, positions, material, is_dynamic, color, density, pressure, velocity,
+                          slab_rows=(int(_shell_z_counts(masks).sum()), rows))
 
     def compute_cube_particle_num(self, start, end, space=None):
         if space is None:
@@ -518,7 +613,10 @@ class BaseContainer:
     def compute_box_particle_num(self, lower_corner, cube_size, thickness, space=None):
         if space is None:
             space = self.particle_diameter
-        return self._box_shell(lower_corner, cube_size, thickness, space).shape[0]
+        if self.dim != 3:
+            return self._box_shell(lower_corner, cube_size, thickness, space).shape[0]
+        axes = _lattice_axes(lower_corner, cube_size, space, self.dim)   # counted per axis: no lattice is built
+        return int(_shell_z_counts(_shell_masks(axes, lower_corner, cube_size, thickness)).sum())
 
     # ------------------------------------------------------------------ mesh bodies
     def load_rigid_body(self, rigid_body, pitch=None):

@@ -80,9 +80,12 @@ class SlabContext:
     def z_hi(self) -> int:
         return self.ranges[self.rank][1]
 
-    def owned(self, positions: np.ndarray) -> np.ndarray:
-        cz = cell_layer(positions[:, 2], self.dh, self.nz)
+    def owned_z(self, z: np.ndarray) -> np.ndarray:
+        cz = cell_layer(z, self.dh, self.nz)
         return (cz >= self.z_lo) & (cz < self.z_hi)
+
+    def owned(self, positions: np.ndarray) -> np.ndarray:
+        return self.owned_z(positions[:, 2])
 
     def capacity(self, layer_counts: Sequence[int], slack: Optional[float] = None, extra: int = 65536) -> int:
         """Local particle capacity: owned layers + one ghost layer each side, with head-room for

@@ -155,3 +155,128 @@ def test_balanced_ranges_properties():
                 assert sum(counts[lo:hi]) <= total / world + 2 * heaviest
 
     check()
+
+
+# ---------------------------------------------------------------- slab-local scene generation
+def _random_boxes(seed, n):
+    rng = np.random.default_rng(seed)
+    for _ in range(n):
+        lower = rng.uniform(-0.3, 0.5, 3)
+        extent = rng.uniform(0.15, 0.9, 3)
+        space = float(rng.choice([0.02, 0.025, 0.04, 0.0125 * 4]))
+        yield lower, extent, space, float(rng.choice([0.03, 0.05, 0.0]))
+
+
+def test_lattice_rows_equal_the_filtered_full_lattice():
+    """A Z-slab rank builds the lattice rows of its own z indices only: same positions (bitwise), same row numbers as
+    building everything and filtering (what every rank did before)."""
+    from sph_project_b200.containers.base_container import _lattice, _lattice_axes, _lattice_rows
+    for lower, extent, space, _ in _random_boxes(1, 12):
+        full = _lattice(lower, extent, space, 3)
+        axes = _lattice_axes(lower, extent, space, 3)
+        nzv = len(axes[2])
+        for kz in (np.arange(nzv), np.arange(nzv // 3, 2 * nzv // 3), np.array([0, nzv - 1]), np.array([], dtype=np.int64)):
+            pos, rows = _lattice_rows(axes, kz)
+            z_index = np.arange(full.shape[0]) % nzv
+            expect = np.flatnonzero(np.isin(z_index, kz))
+            assert np.array_equal(rows, expect)
+            assert pos.dtype == np.float32 and np.array_equal(pos, full[expect])
+
+
+def test_shell_rows_equal_the_filtered_full_shell():
+    from sph_project_b200.containers.base_container import (_lattice, _lattice_axes, _shell_masks, _shell_rows,
+                                                            _shell_z_counts)
+    cases = list(_random_boxes(2, 12))
+    cases.append((np.array([0.0 + 0.04] * 3), np.array([8.5 - 0.08, 8.0 - 0.08, 2.0 - 0.08]) / 4, 0.02, 0.03))   # np.float64 corners
+    cases.append(([0.04, 0.04, 0.04], [0.52, 0.72, 1.12], 0.02, 0.03))                                            # python floats
+    for lower, extent, space, thickness in cases:
+        full = _lattice(lower, extent, space, 3)
+        mask = np.zeros(full.shape[0], dtype=bool)
+        for i in range(3):   # the container's _box_shell (base_container.py:830-835 upstream)
+            mask |= (full[:, i] <= lower[i] + thickness) | (full[:, i] >= lower[i] + extent[i] - thickness)
+        shell = full[mask]
+        shell_row_of = np.cumsum(mask) - 1
+        axes = _lattice_axes(lower, extent, space, 3)
+        masks = _shell_masks(axes, lower, extent, thickness)
+        nzv = len(axes[2])
+        per_z = _shell_z_counts(masks)
+        assert per_z.sum() == shell.shape[0]
+        assert np.array_equal(per_z, np.bincount(np.flatnonzero(mask) % nzv, minlength=nzv))
+        for kz in (np.arange(nzv), np.arange(nzv // 4, nzv // 2), np.array([0, 1, nzv - 2, nzv - 1]), np.array([], dtype=np.int64)):
+            pos, rows = _shell_rows(axes, masks, kz)
+            expect_full_rows = np.flatnonzero(mask & np.isin(np.arange(full.shape[0]) % nzv, kz))
+            assert np.array_equal(rows, shell_row_of[expect_full_rows])
+            assert pos.dtype == np.float32 and np.array_equal(pos, full[expect_full_rows])
+
+
+def test_slab_container_inserts_only_its_layers(monkeypatch):
+    """The container of a slab rank (engine: the CPU oracle, slab calls faked) inserts exactly the particles the unsharded
+    container holds in that rank's layers, with the unsharded insertion indices as uids; the layer histogram it cuts the
+    scene by equals the histogram of the unsharded particles."""
+    import copy
+    import types
+    from helpers import oracle_library
+    from sph_project_b200._native import F
+    from sph_project_b200.containers import DFSPHContainer
+    from sph_project_b200.utils import SimConfig
+    sc = scene("dfsph", domain_end=(0.6, 0.8, 1.2), block_start=(0.1, 0.1, 0.1), block_end=(0.3, 0.5, 1.1), dt=1e-3)
+    lib = oracle_library()
+
+    def build():
+        return DFSPHContainer(SimConfig(config=copy.deepcopy(sc), verbose=False), GGUI=False, engine_library=lib)
+
+    ref = build()
+    ref.insert_object()
+    n = ref.particle_num[None]
+    x_ref, obj_ref = ref.engine.get_field(F.POSITION, n), ref.engine.get_field(F.OBJECT_ID, n)
+    assert np.array_equal(ref.engine.get_field(F.UID, n), np.arange(n))
+    nz = int(ref.grid_num[2])
+    layers = cell_layer(x_ref[:, 2], ref.dh, nz)
+
+    hist = sum(c for c, _ in ref._scene_layers(nz))
+    assert np.array_equal(hist, np.bincount(layers, minlength=nz))
+    fluid_hist = sum(c for c, is_fluid in ref._scene_layers(nz) if is_fluid)
+    assert fluid_hist.sum() == ref.fluid_particle_num[None]
+
+    # the slab calls of the library, faked on the oracle's engine class (the oracle always holds the whole domain)
+    import sph_project_b200._native as nat
+    import sph_project_b200.slab as slab_mod
+    from sph_project_b200.containers.base_container import BaseContainer
+    totals = []
+    monkeypatch.setattr(nat.Engine, "slab_unique_id", lambda self: bytes(128))
+    monkeypatch.setattr(nat.Engine, "slab_init", lambda self, rank, world, uid, z_lo, z_hi, n_global: setattr(self, "_fake_range", (z_lo, z_hi)))
+    monkeypatch.setattr(nat.Engine, "slab_info", lambda self: types.SimpleNamespace(z_lo=self._fake_range[0], z_hi=self._fake_range[1]))
+    monkeypatch.setattr(nat.Engine, "slab_set_global_particle_num", lambda self, v: totals.append(v))
+    monkeypatch.setattr(slab_mod, "broadcast_bytes", lambda payload, nbytes, src=0: payload)
+    monkeypatch.setattr(BaseContainer, "_connect_slab_peers", lambda self: None)
+    make_params = BaseContainer._make_params
+    monkeypatch.setattr(BaseContainer, "_make_params", lambda self, device, slab: make_params(self, device, False))
+
+    world, seen, cuts = 3, 0, None
+    for rank in range(world):
+        c = DFSPHContainer(SimConfig(config=copy.deepcopy(sc), verbose=False), GGUI=False, engine_library=lib, slab=(rank, world))
+        assert cuts is None or cuts == c.slab.ranges
+        cuts = c.slab.ranges
+        assert np.array_equal(c._layer_counts, hist)
+        z_lo, z_hi = cuts[rank]
+        c.insert_object()
+        m = c.particle_num[None]
+        mine = np.flatnonzero((layers >= z_lo) & (layers < z_hi))
+        assert m == mine.size and totals[-1] == n
+        assert np.array_equal(c.engine.get_field(F.UID, m), mine)
+        assert np.array_equal(c.engine.get_field(F.POSITION, m), x_ref[mine])
+        assert np.array_equal(c.engine.get_field(F.OBJECT_ID, m), obj_ref[mine])
+        assert c.fluid_particle_num[None] == ref.fluid_particle_num[None]   # scene totals, as before
+        seen += m
+    assert seen == n and cuts[0][0] == 0 and cuts[-1][1] == nz
+
+
+def test_box_particle_count_without_building_the_box():
+    from helpers import oracle_library
+    from sph_project_b200.containers import DFSPHContainer
+    from sph_project_b200.utils import SimConfig
+    c = DFSPHContainer(SimConfig(config=scene("dfsph", domain_end=(0.7, 0.5, 0.9), dt=1e-3), verbose=False), GGUI=False,
+                       engine_library=oracle_library())
+    for lower, size, t, space in (([0.04] * 3, [0.62, 0.42, 0.82], 0.03, 0.02), (c.domain_box_start, c.domain_box_size, 0.03, 0.02),
+                                  ([0.0, 0.1, 0.2], [0.3, 0.3, 0.3], 0.05, 0.025)):
+        assert c.compute_box_particle_num(lower, size, t, space) == c._box_shell(lower, size, t, space).shape[0]
