@@ -43,12 +43,6 @@
 #ifndef SPH_BRICK_THREADS
 #define SPH_BRICK_THREADS 512
 #endif
-// Neighbours whose shared-memory loads are issued together.  Measured on B200 (profiles/r02_brick_experiments.md):
-// batches of 4 need 64 registers, i.e. two instead of three resident CTAs per SM, and lose more to the missing warps
-// (186 / 202 us per correction / density-change sweep) than they gain from the overlap (168 / 181 us unbatched).
-#ifndef SPH_BRICK_ILP
-#define SPH_BRICK_ILP 1
-#endif
 
 constexpr int BRK_X = SPH_BRICK_X, BRK_Y = SPH_BRICK_Y, BRK_Z = SPH_BRICK_Z;
 constexpr int BRK_RY = BRK_Y + 2, BRK_RZ = BRK_Z + 2;
@@ -457,8 +451,7 @@ __device__ __forceinline__ float4 brick_payload1(const Brick& bk, int j) {
 // All neighbours j of owned particle i in walk order: visit(ref, pj, aj, bj, R, r2), aj / bj = entry j of the second /
 // third staged array (pv_j itself when the sweep stages fewer).  Returns the number of neighbours.
 // A_HALF: the visitor reads only the first two components of aj (64-bit shared loads).
-// ILP: neighbours whose shared-memory loads are issued together (registers permitting).
-template <bool LIST, bool NC, int NARR, bool A_HALF = false, int ILP = SPH_BRICK_ILP, class Visit>
+template <bool LIST, bool NC, int NARR, bool A_HALF = false, class Visit>
 __device__ __forceinline__ int brick_neighbors(const Consts& c, const Dev& d, const Brick& bk, int i, float4 pi, Visit&& visit) {
     if (LIST) {
         const unsigned short* row = d.nbr16 + (size_t)i * d.nbr_kmax;
@@ -474,86 +467,22 @@ __device__ __forceinline__ int brick_neighbors(const Consts& c, const Dev& d, co
                 asm volatile("mov.u32 %0, %0;" : "+r"(a0));
                 if (NARR > 1) asm volatile("mov.u32 %0, %0;" : "+r"(a1));
                 if (NARR > 2) asm volatile("mov.u32 %0, %0;" : "+r"(a2));
-                // One 256-bit load per 16 words, then batches of ILP neighbours: all shared-memory loads of a
-                // batch are issued before the first neighbour is evaluated (the per-neighbour branches would otherwise
-                // keep the compiler from overlapping them; measured: short-scoreboard stalls on one LDS at a time).
-                // Words past the end of the list load slot 0 (always inside the window) and are skipped.
+                // One 256-bit load per 16 list words, one neighbour at a time.  Issuing the shared-memory loads of 2-4
+                // neighbours together, or one neighbour ahead, was measured slower (batches of 4 need 64 registers, i.e.
+                // 2 resident CTAs per SM instead of 3: 186 / 202 us per correction / density-change sweep against
+                // 168 / 181 us; profiles/r02_brick_experiments.md).
                 int base = 0;
 #pragma unroll 1
                 for (;;) {
-#ifdef SPH_BRICK_ROLLING
-                    if (ILP == 1) {
-                        // rolling prefetch: neighbour u + 1's window entries are requested before neighbour u is evaluated
-                        bool ok_n = base > 0 && base <= n;
-                        unsigned off_n = (w[0] << 4) & 0xffff0u;
-                        float4 pj_n = make_float4(0.f, 0.f, 0.f, 0.f), aj_n = pj_n, bj_n = pj_n;
-                        if (ok_n) {
-                            pj_n = lds128(a0 + off_n);
-                            if (NARR > 1) aj_n = A_HALF ? lds64(a1 + off_n) : lds128(a1 + off_n);
-                            if (NARR > 2) bj_n = lds128(a2 + off_n);
-                        }
 #pragma unroll
-                        for (int u = 0; u < 16; u++) {
-                            const bool ok = ok_n;
-                            const unsigned off = off_n;
-                            const float4 pj = pj_n;
-                            const float4 aj = NARR > 1 ? aj_n : pj_n;
-                            const float4 bj = NARR > 2 ? bj_n : pj_n;
-                            if (u + 1 < 16) {
-                                ok_n = base + u + 1 <= n;
-                                off_n = ((u + 1) & 1) ? ((w[(u + 1) >> 1] >> 12) & 0xffff0u) : ((w[(u + 1) >> 1] << 4) & 0xffff0u);
-                                if (ok_n) {
-                                    pj_n = lds128(a0 + off_n);
-                                    if (NARR > 1) aj_n = A_HALF ? lds64(a1 + off_n) : lds128(a1 + off_n);
-                                    if (NARR > 2) bj_n = lds128(a2 + off_n);
-                                }
-                            }
-                            if (ok) {
-                                const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-                                visit(NbrRef{(int)(off >> 4), true}, pj, aj, bj, R, dist2(R));
-                            }
-                        }
-                    } else
-#endif
-                    if (ILP == 1) {
-#pragma unroll
-                        for (int u = 0; u < 16; u++) {
-                            if ((u > 0 || base > 0) && base + u <= n) {
-                                const unsigned off = (u & 1) ? ((w[u >> 1] >> 12) & 0xffff0u) : ((w[u >> 1] << 4) & 0xffff0u);   // 16 x slot
-                                const float4 pj = lds128(a0 + off);
-                                const float4 aj = NARR > 1 ? (A_HALF ? lds64(a1 + off) : lds128(a1 + off)) : pj;
-                                const float4 bj = NARR > 2 ? lds128(a2 + off) : pj;
-                                const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
-                                visit(NbrRef{(int)(off >> 4), true}, pj, aj, bj, R, dist2(R));
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int u0 = 0; u0 < 16; u0 += ILP) {
-                            if (base + u0 > n) break;
-                            unsigned off[ILP];
-                            bool ok[ILP];
-                            float4 pj[ILP], aj[ILP], bj[ILP];
-    #pragma unroll
-                            for (int k = 0; k < ILP; k++) {
-                                const int u = u0 + k;
-                                ok[k] = (u > 0 || base > 0) && base + u <= n;
-                                const unsigned o16 = (u & 1) ? ((w[u >> 1] >> 12) & 0xffff0u) : ((w[u >> 1] << 4) & 0xffff0u);   // 16 x slot
-                                off[k] = ok[k] ? o16 : 0u;
-                            }
-    #pragma unroll
-                            for (int k = 0; k < ILP; k++) {
-                                pj[k] = lds128(a0 + off[k]);
-                                aj[k] = NARR > 1 ? (A_HALF ? lds64(a1 + off[k]) : lds128(a1 + off[k])) : pj[k];
-                                bj[k] = NARR > 2 ? lds128(a2 + off[k]) : pj[k];
-                            }
-    #pragma unroll
-                            for (int k = 0; k < ILP; k++) {
-                                if (ok[k]) {
-                                    const float3 R = make_float3(pi.x - pj[k].x, pi.y - pj[k].y, pi.z - pj[k].z);
-                                    visit(NbrRef{(int)(off[k] >> 4), true}, pj[k], aj[k], bj[k], R, dist2(R));
-                                }
-                            }
+                    for (int u = 0; u < 16; u++) {
+                        if ((u > 0 || base > 0) && base + u <= n) {
+                            const unsigned off = (u & 1) ? ((w[u >> 1] >> 12) & 0xffff0u) : ((w[u >> 1] << 4) & 0xffff0u);   // 16 x slot
+                            const float4 pj = lds128(a0 + off);
+                            const float4 aj = NARR > 1 ? (A_HALF ? lds64(a1 + off) : lds128(a1 + off)) : pj;
+                            const float4 bj = NARR > 2 ? lds128(a2 + off) : pj;
+                            const float3 R = make_float3(pi.x - pj.x, pi.y - pj.y, pi.z - pj.z);
+                            visit(NbrRef{(int)(off >> 4), true}, pj, aj, bj, R, dist2(R));
                         }
                     }
                     base += 16;
