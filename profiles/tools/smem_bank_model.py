@@ -60,9 +60,10 @@ def wavefronts(slots, lanes_per_phase):
     return total
 
 
-def main():
-    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 600
-    x, fluid, uid, g, cell_size, h, _ = settled_state(steps)
+def brick_lists(x, fluid, uid, g, cell_size, h):
+    """Replay of the brick layout on a particle state.  Returns (order, bricks): `order` = the sort permutation, `bricks`
+    = per active brick (rows, lists, slot_to_index, window_slots) with rows = sorted indices of its fluid particles in
+    owned order, lists[k] = window slots of row k's neighbours in walk order, slot_to_index = sorted index of each slot."""
     n = x.shape[0]
     cell = np.minimum(np.maximum((x / cell_size).astype(np.int64), 0), g - 1)
     flat = (cell[:, 2] * g[1] + cell[:, 1]) * g[0] + cell[:, 0]
@@ -71,8 +72,7 @@ def main():
     ncell = int(g.prod())
     start = np.searchsorted(flat, np.arange(ncell + 1))          # cell_start of the sorted arrays
     h2 = np.float32(h) * np.float32(h)
-
-    rows_per_brick, lists, window_sizes = [], [], []
+    bricks = []
     nb = [-(-int(g[0]) // BX), -(-int(g[1]) // BY), -(-int(g[2]) // BZ)]
     for bz in range(nb[2]):
         for by in range(nb[1]):
@@ -101,7 +101,6 @@ def main():
                 own = own[fluid[own]]
                 if own.size == 0:
                     continue
-                window_sizes.append(int(S[-1]))
                 brick_rows = []
                 for i in own:
                     cx, cy, cz = cell[i]
@@ -119,8 +118,19 @@ def main():
                         acc = ((d * d).sum(axis=1) < h2) & (j != i)
                         out.append(S[r] + (j[acc] - run_lo[r]))
                     brick_rows.append(np.concatenate(out) if out else np.zeros(0, np.int64))
-                rows_per_brick.append(len(brick_rows))
-                lists.append(brick_rows)
+                slot_to_index = np.concatenate([np.arange(run_lo[r], run_hi[r]) for r in range(RY * RZ)])
+                bricks.append((own, brick_rows, slot_to_index, int(S[-1])))
+    return order, bricks
+
+
+def main():
+    steps = int(sys.argv[1]) if len(sys.argv) > 1 else 600
+    x, fluid, uid, g, cell_size, h, _ = settled_state(steps)
+    n = x.shape[0]
+    _, bricks = brick_lists(x, fluid, uid, g, cell_size, h)
+    lists = [b[1] for b in bricks]
+    rows_per_brick = [len(b[1]) for b in bricks]
+    window_sizes = [b[3] for b in bricks]
 
     counts = np.array([len(r) for b in lists for r in b])
     pairs = int(counts.sum())
